@@ -1,0 +1,226 @@
+// extern "C" entry points of libep_b200.so (declared in include/ep_b200.h): argument checking,
+// workspace carving and kernel-family dispatch.  No allocation, no host synchronisation.
+#include "ep_common.cuh"
+#include "ep_sm100.cuh"
+
+using namespace ep;
+
+unsigned long long ep::g_launch_count = 0;
+static int g_kernel_mode = 0;                 // 0 auto, 1 general, 2 tcgen05
+static thread_local int t_last_family = 0;
+
+extern "C" int ep_abi_version(void) { return EP_ABI_VERSION; }
+
+extern "C" const char* ep_strerror(int code) {
+  switch (code) {
+    case EP_OK: return "ok";
+    case EP_ERR_NULL: return "required pointer is NULL";
+    case EP_ERR_SHAPE: return "invalid shape (sizes must be positive and D divisible by d_out*num_queries)";
+    case EP_ERR_ALIGN: return "D must be a multiple of 8 and pointers 16-byte aligned";
+    case EP_ERR_DTYPE: return "token dtype must be bf16 (0) or fp32 (1)";
+    case EP_ERR_WORKSPACE: return "workspace smaller than ep_workspace_bytes()";
+    case EP_ERR_UNSUPPORTED: return "shape not supported by the selected kernel family";
+    case EP_ERR_DEVICE: return "current CUDA device is not compute capability 10.x (B200)";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown ep_status";
+  }
+}
+
+extern "C" int ep_device_check(void) {
+  int dev = 0, major = 0;
+  EP_CUDA(cudaGetDevice(&dev));
+  EP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? 0 : EP_ERR_DEVICE;
+}
+
+extern "C" int ep_set_kernel_mode(int mode) {
+  if (mode < 0 || mode > 2) return EP_ERR_SHAPE;
+  g_kernel_mode = mode;
+  return 0;
+}
+extern "C" int ep_last_kernel_family(void) { return t_last_family; }
+extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count; }
+
+namespace {
+struct Ws {                      // backward workspace layout
+  size_t dP, delta, slots, sm100, total;
+};
+Ws carve(int B, int N, int D, int M) {
+  Ws w;
+  size_t off = 0;
+  w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
+  w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
+  w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
+  w.sm100 = off; off += align_up(sm100_workspace_bytes(B, N, D, M), 256);
+  w.total = off;
+  return w;
+}
+int check_common(const void* x, int x_dtype, const float* cls, int B, int N, int D, int M, int d_out) {
+  if (!x || !cls) return EP_ERR_NULL;
+  if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0) return EP_ERR_SHAPE;
+  if (D % (d_out * M) != 0) return EP_ERR_SHAPE;
+  if (D % 8 != 0) return EP_ERR_ALIGN;
+  if (x_dtype != EP_DTYPE_BF16 && x_dtype != EP_DTYPE_F32) return EP_ERR_DTYPE;
+  if (((uintptr_t)x & 15) || ((uintptr_t)cls & 15)) return EP_ERR_ALIGN;
+  return 0;
+}
+bool use_sm100(int x_dtype, int B, int N, int D, int M, int* rc) {
+  *rc = 0;
+  if (g_kernel_mode == 1) return false;
+  const bool ok = sm100_supported(x_dtype, B, N, D, M);
+  if (g_kernel_mode == 2 && !ok) *rc = EP_ERR_UNSUPPORTED;
+  return ok;
+}
+}  // namespace
+
+extern "C" size_t ep_workspace_bytes(int B, int N, int D, int M, int d_out) {
+  (void)d_out;
+  if (B <= 0 || N <= 0 || D <= 0 || M <= 0) return 0;
+  return carve(B, N, D, M).total;
+}
+
+extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
+                      float scale, int B, int N, int D, int M, int d_out, float* out, float* rowmax, float* rowsum,
+                      float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
+  if (rc) return rc;
+  if (!v_w || !out || !rowmax || !rowsum || !P) return EP_ERR_NULL;
+  const Ws w = carve(B, N, D, M);
+  if (w.total > 0 && (!workspace || workspace_bytes < w.total)) return EP_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (use_sm100(x_dtype, B, N, D, M, &rc)) {
+    t_last_family = 2;
+    rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, rowmax, rowsum, attn, (char*)workspace + w.sm100, s);
+  } else {
+    if (rc) return rc;
+    t_last_family = 1;
+    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, rowmax, rowsum, attn, s);
+  }
+  if (rc) return rc;
+  // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
+  const int Dp = D / d_out, c = Dp / M;
+  GemmDesc g{};
+  g.A = P; g.B = v_w; g.C = out; g.bias = v_b;
+  g.I = B; g.J = c; g.K = D; g.Z = M;
+  g.a_i = (long long)M * D; g.a_k = 1; g.a_z = D;
+  g.b_k = 1; g.b_j = D; g.b_z = (long long)c * D;
+  g.c_i = Dp; g.c_j = 1; g.c_z = c; g.bias_z = c;
+  return launch_gemm_v0(g, s);
+}
+
+extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int B, int N, int D, int M,
+                           int d_out, float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (!g_out || !P || !v_w || !d_v_w) return EP_ERR_NULL;
+  if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
+  const Ws w = carve(B, N, D, M);
+  if (!workspace || workspace_bytes < w.total) return EP_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* dP = (float*)((char*)workspace + w.dP);
+  float* delta = (float*)((char*)workspace + w.delta);
+  const int Dp = D / d_out, c = Dp / M;
+  int rc;
+  {  // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]
+    GemmDesc g{};
+    g.A = g_out; g.B = P; g.C = d_v_w;
+    g.I = c; g.J = D; g.K = B; g.Z = M;
+    g.a_i = 1; g.a_k = Dp; g.a_z = c;
+    g.b_k = (long long)M * D; g.b_j = 1; g.b_z = D;
+    g.c_i = D; g.c_j = 1; g.c_z = (long long)c * D;
+    if ((rc = launch_gemm_v0(g, s))) return rc;
+  }
+  if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
+  {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]
+    GemmDesc g{};
+    g.A = g_out; g.B = v_w; g.C = dP;
+    g.I = B; g.J = D; g.K = c; g.Z = M;
+    g.a_i = Dp; g.a_k = 1; g.a_z = c;
+    g.b_k = D; g.b_j = 1; g.b_z = (long long)c * D;
+    g.c_i = (long long)M * D; g.c_j = 1; g.c_z = D;
+    if ((rc = launch_gemm_v0(g, s))) return rc;
+  }
+  return launch_rowdot(dP, P, (long long)B * M, D, delta, s);   // delta = sum_n A dA = dP . P
+}
+
+extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M,
+                           int d_out, const float* rowmax, const float* rowsum, float* d_cls_token, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
+  if (rc) return rc;
+  if (!rowmax || !rowsum || !d_cls_token) return EP_ERR_NULL;
+  const Ws w = carve(B, N, D, M);
+  if (!workspace || workspace_bytes < w.total) return EP_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* dP = (const float*)((char*)workspace + w.dP);
+  const float* delta = (const float*)((char*)workspace + w.delta);
+  float* slots = (float*)((char*)workspace + w.slots);
+  if (use_sm100(x_dtype, B, N, D, M, &rc)) {
+    t_last_family = 2;
+    return sm100_pool_bwd(x, cls_token, scale, B, N, D, M, rowmax, rowsum, dP, delta, d_cls_token,
+                          (char*)workspace + w.sm100, s);
+  }
+  if (rc) return rc;
+  t_last_family = 1;
+  return pool_bwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, rowmax, rowsum, dP, delta, slots, kDqSlots,
+                     d_cls_token, s);
+}
+
+extern "C" int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale, int B, int N,
+                      int D, int M, int d_out, const float* rowmax, const float* rowsum, const float* P,
+                      const float* g_out, float* d_cls_token, float* d_v_w, float* d_v_b, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
+  if (rc) return rc;
+  if (!v_w || !rowmax || !rowsum || !P || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
+  if ((rc = ep_bwd_proj(g_out, P, v_w, B, N, D, M, d_out, d_v_w, d_v_b, workspace, workspace_bytes, stream))) return rc;
+  return ep_bwd_pool(x, x_dtype, cls_token, scale, B, N, D, M, d_out, rowmax, rowsum, d_cls_token, workspace,
+                     workspace_bytes, stream);
+}
+
+extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D,
+                                 int M, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, x_dtype, cls_token, B, N, D, M, 1);
+  if (rc == EP_ERR_SHAPE && B > 0 && N > 0 && D > 0 && M > 0) rc = (D % 8) ? EP_ERR_ALIGN : 0;  // no channel split here
+  if (rc) return rc;
+  if (!attn) return EP_ERR_NULL;
+  const size_t need = align_up((size_t)2 * B * M * sizeof(float), 256);
+  if (!workspace || workspace_bytes < need) return EP_ERR_WORKSPACE;
+  float* rowmax = (float*)workspace;
+  float* rowsum = rowmax + (size_t)B * M;
+  t_last_family = 1;
+  return pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, nullptr, rowmax, rowsum, attn, (cudaStream_t)stream);
+}
+
+extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
+                             void* stream) {
+  if (!y || !W || !logits) return EP_ERR_NULL;
+  GemmDesc g{};
+  g.A = y; g.B = W; g.C = logits; g.bias = b;
+  g.I = B; g.J = K; g.K = F; g.Z = 1;
+  g.a_i = F; g.a_k = 1; g.b_k = 1; g.b_j = F; g.c_i = K; g.c_j = 1;
+  return launch_gemm_v0(g, (cudaStream_t)stream);
+}
+
+extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* W, int B, int F, int K, float* dW,
+                             float* db, float* dy, void* stream) {
+  if (!dlogits) return EP_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (dW) {
+    if (!y) return EP_ERR_NULL;
+    GemmDesc g{};
+    g.A = dlogits; g.B = y; g.C = dW;
+    g.I = K; g.J = F; g.K = B; g.Z = 1;
+    g.a_i = 1; g.a_k = K; g.b_k = F; g.b_j = 1; g.c_i = F; g.c_j = 1;
+    if ((rc = launch_gemm_v0(g, s))) return rc;
+  }
+  if (db && (rc = launch_colsum(dlogits, B, K, db, s))) return rc;
+  if (dy) {
+    if (!W) return EP_ERR_NULL;
+    GemmDesc g{};
+    g.A = dlogits; g.B = W; g.C = dy;
+    g.I = B; g.J = F; g.K = K; g.Z = 1;
+    g.a_i = K; g.a_k = 1; g.b_k = F; g.b_j = 1; g.c_i = F; g.c_j = 1;
+    if ((rc = launch_gemm_v0(g, s))) return rc;
+  }
+  return 0;
+}

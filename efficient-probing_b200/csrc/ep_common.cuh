@@ -1,0 +1,79 @@
+// Shared helpers for the libep_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/ep_b200.h"
+
+// every kernel launch in the library is followed by this: error check + launch accounting
+#define EP_LAUNCH_CHECK()                                  \
+  do {                                                     \
+    ++ep::g_launch_count;                                  \
+    cudaError_t e__ = cudaGetLastError();                  \
+    if (e__ != cudaSuccess) return (int)e__;               \
+  } while (0)
+
+#define EP_CUDA(call)                                      \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) return (int)e__;               \
+  } while (0)
+
+namespace ep {
+
+extern unsigned long long g_launch_count;     // kernels launched by this library in this process
+constexpr int kNumSMs = 148;
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 8 consecutive token channels as floats, from bf16 (one 128-bit load) or fp32 (two).
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
+  uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// ---- internal launchers shared between translation units (all return ep_status / cudaError) ----
+struct GemmDesc {      // C[z][i][j] = sum_k A[z][i][k] * B[z][k][j] (+ bias[z][j]); element strides
+  const float* A; const float* B; float* C; const float* bias;
+  int I, J, K, Z;
+  long long a_i, a_k, a_z, b_k, b_j, b_z, c_i, c_j, c_z, bias_z;
+};
+int launch_gemm_v0(const GemmDesc& g, cudaStream_t s);
+int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s);            // out[j] = sum_i a[i][j]
+int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s);  // out[i] = a[i].b[i]
+
+int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
+                float* P, float* rowmax, float* rowsum, float* attn, cudaStream_t s);
+int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
+                const float* rowmax, const float* rowsum, const float* dP, const float* delta,
+                float* dq_slots, int n_slots, float* d_cls, cudaStream_t s);
+size_t pool_v0_smem_bytes(int N, int M);
+constexpr int kDqSlots = 16;
+
+}  // namespace ep

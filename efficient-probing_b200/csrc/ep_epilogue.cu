@@ -1,0 +1,232 @@
+// Small head kernels after the pooling: BatchNorm1d(affine=False), cross-entropy forward+backward,
+// fused multi-tensor LARS.  All fp32.
+#include "ep_common.cuh"
+
+namespace ep {
+
+// ---------------- BatchNorm1d(affine=False, eps) -- probe_heads.py:109-110 ----------------
+// one CTA per 32 features, 32x32 threads: x = feature (coalesced), y strides the batch.
+__device__ __forceinline__ float block_colsum(float v, float (*red)[33]) {
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x];
+    red[0][threadIdx.x] = t;
+  }
+  __syncthreads();
+  const float r = red[0][threadIdx.x];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024)
+bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float momentum, int training,
+              float* __restrict__ running_mean, float* __restrict__ running_var, long long* nbt,
+              float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  __shared__ float red[32][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = f < F;
+  float mean, invstd;
+  if (training) {
+    float s = 0.f;
+    if (ok) for (int b = threadIdx.y; b < B; b += 32) s += h[(size_t)b * F + f];
+    mean = block_colsum(s, red) / B;
+    float v = 0.f;
+    if (ok) for (int b = threadIdx.y; b < B; b += 32) { const float d = h[(size_t)b * F + f] - mean; v = fmaf(d, d, v); }
+    const float var = block_colsum(v, red) / B;                    // biased, used to normalise
+    invstd = rsqrtf(var + eps);
+    if (ok && threadIdx.y == 0) {
+      const float unbiased = B > 1 ? var * ((float)B / (float)(B - 1)) : var;
+      running_mean[f] = (1.f - momentum) * running_mean[f] + momentum * mean;
+      running_var[f] = (1.f - momentum) * running_var[f] + momentum * unbiased;
+      if (save_mean) save_mean[f] = mean;
+      if (save_invstd) save_invstd[f] = invstd;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt) *nbt += 1;
+  } else {
+    mean = ok ? running_mean[f] : 0.f;
+    invstd = ok ? 1.f / sqrtf(running_var[f] + eps) : 0.f;
+  }
+  if (ok) for (int b = threadIdx.y; b < B; b += 32) y[(size_t)b * F + f] = (h[(size_t)b * F + f] - mean) * invstd;
+}
+
+__global__ void __launch_bounds__(1024)
+bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ invstd, int B, int F,
+              float* __restrict__ dh) {
+  __shared__ float red[32][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = f < F;
+  float s1 = 0.f, s2 = 0.f;
+  if (ok) for (int b = threadIdx.y; b < B; b += 32) {
+    const float g = dy[(size_t)b * F + f];
+    s1 += g;
+    s2 = fmaf(g, y[(size_t)b * F + f], s2);
+  }
+  const float m1 = block_colsum(s1, red) / B;
+  const float m2 = block_colsum(s2, red) / B;
+  if (ok) {
+    const float is = invstd[f];
+    for (int b = threadIdx.y; b < B; b += 32)
+      dh[(size_t)b * F + f] = is * (dy[(size_t)b * F + f] - m1 - y[(size_t)b * F + f] * m2);
+  }
+}
+
+// ---------------- CrossEntropyLoss (mean) fwd+bwd, one CTA per row ----------------
+__global__ void __launch_bounds__(256)
+ce_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, int K, float loss_scale,
+          float grad_scale, float* loss_sum, float* __restrict__ dlogits, int* correct) {
+  __shared__ float redf[8];
+  __shared__ int redi[8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* row = logits + (size_t)b * K;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float v = row[k];
+    if (v > mx) { mx = v; arg = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  if (lane == 0) { redf[warp] = mx; redi[warp] = arg; }
+  __syncthreads();
+  mx = redf[0]; arg = redi[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w)
+    if (redf[w] > mx || (redf[w] == mx && redi[w] < arg)) { mx = redf[w]; arg = redi[w]; }
+  __syncthreads();
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) s += expf(row[k] - mx);
+  s = warp_sum(s);
+  if (lane == 0) redf[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += redf[w];
+  const int t = (int)targets[b];
+  const float inv = 1.f / s;
+  if (dlogits)
+    for (int k = threadIdx.x; k < K; k += 256)
+      dlogits[(size_t)b * K + k] = (expf(row[k] - mx) * inv - (k == t ? 1.f : 0.f)) * grad_scale;
+  if (threadIdx.x == 0) {
+    if (loss_sum) atomicAdd(loss_sum, (logf(s) + mx - row[t]) * loss_scale);
+    if (correct && arg == t) atomicAdd(correct, 1);
+  }
+}
+
+// ---------------- LARS (util/lars.py:13-37), all tensors in two launches ----------------
+struct LarsArgs {
+  float* p[EP_LARS_MAX_TENSORS];
+  const float* g[EP_LARS_MAX_TENSORS];
+  float* mu[EP_LARS_MAX_TENSORS];
+  long long n[EP_LARS_MAX_TENSORS];
+  int trust[EP_LARS_MAX_TENSORS];
+  int count;
+};
+// hyper = {lr, weight_decay, momentum, trust_coefficient, grad_scale}
+
+__global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float* __restrict__ hyper, float* norms) {
+  const int t = blockIdx.y;
+  if (!a.trust[t]) return;
+  const float wd = hyper[1], gs = hyper[4];
+  float sp = 0.f, su = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
+    const float p = a.p[t][i];
+    const float u = fmaf(wd, p, a.g[t][i] * gs);
+    sp = fmaf(p, p, sp);
+    su = fmaf(u, u, su);
+  }
+  __shared__ float r0[8], r1[8];
+  sp = warp_sum(sp); su = warp_sum(su);
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = sp; r1[threadIdx.x >> 5] = su; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0.f, y = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { x += r0[w]; y += r1[w]; }
+    atomicAdd(norms + 2 * t, x);
+    atomicAdd(norms + 2 * t + 1, y);
+  }
+}
+
+__global__ void __launch_bounds__(256) lars_update_kernel(LarsArgs a, const float* __restrict__ hyper,
+                                                          const float* __restrict__ norms) {
+  const int t = blockIdx.y;
+  const float lr = hyper[0], wd = hyper[1], mom = hyper[2], tc = hyper[3], gs = hyper[4];
+  float q = 1.f;
+  const bool tr = a.trust[t] != 0;
+  if (tr) {
+    const float pn = sqrtf(norms[2 * t]), un = sqrtf(norms[2 * t + 1]);
+    q = (pn > 0.f && un > 0.f) ? tc * pn / un : 1.f;
+  }
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
+    const float p = a.p[t][i];
+    float u = a.g[t][i] * gs;
+    if (tr) u = fmaf(wd, p, u) * q;
+    const float m = fmaf(mom, a.mu[t][i], u);
+    a.mu[t][i] = m;
+    a.p[t][i] = fmaf(-lr, m, p);
+  }
+}
+
+}  // namespace ep
+
+using namespace ep;
+
+extern "C" int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum, int training, float* running_mean,
+                         float* running_var, long long* nbt, float* y, float* save_mean, float* save_invstd,
+                         void* stream) {
+  if (!h || !y || !running_mean || !running_var) return EP_ERR_NULL;
+  if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
+  bn_fwd_kernel<<<(F + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(h, B, F, eps, momentum, training, running_mean,
+                                                                         running_var, nbt, y, save_mean, save_invstd);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ep_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, void* stream) {
+  if (!dy || !y || !save_invstd || !dh) return EP_ERR_NULL;
+  if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
+  bn_bwd_kernel<<<(F + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(dy, y, save_invstd, B, F, dh);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ep_ce_fwd_bwd(const float* logits, const long long* targets, int B, int K, float loss_scale,
+                             float grad_scale, float* loss_sum, float* dlogits, int* correct, void* stream) {
+  if (!logits || !targets) return EP_ERR_NULL;
+  if (B <= 0 || K <= 0) return EP_ERR_SHAPE;
+  ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, targets, K, loss_scale, grad_scale, loss_sum, dlogits, correct);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ep_lars_step(int n, float* const* params, const float* const* grads, float* const* mus,
+                            const long long* numels, const int* apply_trust, const float* hyper, float* scratch,
+                            void* stream) {
+  if (n <= 0 || n > EP_LARS_MAX_TENSORS) return EP_ERR_SHAPE;
+  if (!params || !grads || !mus || !numels || !apply_trust || !hyper || !scratch) return EP_ERR_NULL;
+  LarsArgs a;
+  a.count = n;
+  long long mx = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!params[i] || !grads[i] || !mus[i]) return EP_ERR_NULL;
+    a.p[i] = params[i]; a.g[i] = grads[i]; a.mu[i] = mus[i]; a.n[i] = numels[i]; a.trust[i] = apply_trust[i];
+    if (numels[i] > mx) mx = numels[i];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  EP_CUDA(cudaMemsetAsync(scratch, 0, 2 * n * sizeof(float), s));
+  int bx = (int)((mx + 256 * 8 - 1) / (256 * 8));
+  if (bx < 1) bx = 1;
+  if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+  lars_norm_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch);
+  EP_LAUNCH_CHECK();
+  lars_update_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch);
+  EP_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,222 @@
+// General (any M <= 64, any N that fits shared memory, D % 8 == 0) CUDA-core kernels for the EP
+// pooling: one CTA per sample.  These are the always-available path and the on-device cross-check
+// for the tcgen05 kernels; they read each sample twice (second read from L2).
+//
+//   forward  : S = scale * cls . x^T -> softmax over tokens -> P = A x         (poolings/ep.py:35-44,
+//              with the value projection moved after the pooling)
+//   backward : recompute A from (rowmax,rowsum), dA = dP . x^T, dS = A (dA - delta), dq = dS^T x
+#include "ep_common.cuh"
+
+namespace ep {
+
+constexpr int kThreads = 256;
+constexpr int kMG = 8;       // queries per work item in the logit phase
+
+__host__ __device__ inline int s_ld(int M) { return ((M + 3) & ~3) + 4; }   // row stride of S in smem (floats)
+size_t pool_v0_smem_bytes(int N, int M) { return (size_t)N * s_ld(M) * sizeof(float); }
+
+// logits (and optionally dA) for token pairs x query groups; results left in smem S[n][LD].
+template <typename XT, bool kBwd>
+__device__ __forceinline__ void logit_phase(const XT* __restrict__ xb, const float* __restrict__ cls,
+                                            const float* __restrict__ dPb, float scale, int N, int D, int M,
+                                            const float* __restrict__ rmax, const float* __restrict__ rsum,
+                                            const float* __restrict__ delta, float* S) {
+  const int LD = s_ld(M);
+  const int groups = (M + kMG - 1) / kMG;
+  const int pairs = (N + 1) / 2;
+  for (int item = threadIdx.x; item < pairs * groups; item += kThreads) {
+    const int pr = item / groups, mg = item - pr * groups;
+    const int n0 = 2 * pr, n1 = min(2 * pr + 1, N - 1);
+    const XT* x0 = xb + (size_t)n0 * D;
+    const XT* x1 = xb + (size_t)n1 * D;
+    float s0[kMG], s1[kMG], a0[kMG], a1[kMG];
+#pragma unroll
+    for (int j = 0; j < kMG; ++j) { s0[j] = s1[j] = a0[j] = a1[j] = 0.f; }
+    for (int d = 0; d < D; d += 8) {
+      float v0[8], v1[8];
+      load8(x0 + d, v0);
+      load8(x1 + d, v1);
+#pragma unroll
+      for (int j = 0; j < kMG; ++j) {
+        const int m = min(mg * kMG + j, M - 1);
+        float q[8];
+        load8(cls + (size_t)m * D + d, q);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s0[j] = fmaf(q[e], v0[e], s0[j]); s1[j] = fmaf(q[e], v1[e], s1[j]); }
+        if (kBwd) {
+          load8(dPb + (size_t)m * D + d, q);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { a0[j] = fmaf(q[e], v0[e], a0[j]); a1[j] = fmaf(q[e], v1[e], a1[j]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMG; ++j) {
+      const int m = mg * kMG + j;
+      if (m >= M) break;
+      float r0 = s0[j] * scale, r1 = s1[j] * scale;
+      if (kBwd) {
+        const float mx = rmax[m], inv = 1.f / rsum[m], dl = delta[m];
+        r0 = expf(r0 - mx) * inv * (a0[j] - dl);
+        r1 = expf(r1 - mx) * inv * (a1[j] - dl);
+      }
+      S[n0 * LD + m] = r0;
+      if (2 * pr + 1 < N) S[n1 * LD + m] = r1;
+    }
+  }
+}
+
+// acc[m][0..1] += sum_n W[n][m] * x[n][dd..dd+1] for a block of <= 32 queries; W in smem.
+template <typename XT>
+__device__ __forceinline__ void pool_phase(const XT* __restrict__ xb, const float* S, int N, int D, int M,
+                                           int mb, int dd, float (&acc)[32][2]) {
+  const int LD = s_ld(M);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j][0] = acc[j][1] = 0.f;
+  const int mcount = min(32, M - mb);
+  const int quads = (mcount + 3) / 4;
+  for (int n = 0; n < N; ++n) {
+    const float2 xv = load2(xb + (size_t)n * D + dd);
+    const float4* row = reinterpret_cast<const float4*>(S + n * LD + mb);
+#pragma unroll
+    for (int qd = 0; qd < 8; ++qd) {
+      if (qd < quads) {
+        const float4 w = row[qd];
+        acc[4 * qd + 0][0] = fmaf(w.x, xv.x, acc[4 * qd + 0][0]); acc[4 * qd + 0][1] = fmaf(w.x, xv.y, acc[4 * qd + 0][1]);
+        acc[4 * qd + 1][0] = fmaf(w.y, xv.x, acc[4 * qd + 1][0]); acc[4 * qd + 1][1] = fmaf(w.y, xv.y, acc[4 * qd + 1][1]);
+        acc[4 * qd + 2][0] = fmaf(w.z, xv.x, acc[4 * qd + 2][0]); acc[4 * qd + 2][1] = fmaf(w.z, xv.y, acc[4 * qd + 2][1]);
+        acc[4 * qd + 3][0] = fmaf(w.w, xv.x, acc[4 * qd + 3][0]); acc[4 * qd + 3][1] = fmaf(w.w, xv.y, acc[4 * qd + 3][1]);
+      }
+    }
+  }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(kThreads)
+pool_fwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, float scale, int N, int D, int M,
+                   float* __restrict__ P, float* __restrict__ rowmax, float* __restrict__ rowsum,
+                   float* __restrict__ attn) {
+  extern __shared__ __align__(16) float S[];
+  const int b = blockIdx.x, LD = s_ld(M);
+  const XT* xb = x + (size_t)b * N * D;
+  // zero the pad columns so the float4 reads of the pooling phase never see garbage
+  for (int i = threadIdx.x; i < N * LD; i += kThreads) S[i] = 0.f;
+  __syncthreads();
+  logit_phase<XT, false>(xb, cls, nullptr, scale, N, D, M, nullptr, nullptr, nullptr, S);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = warp; m < M; m += kThreads / 32) {
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, S[n * LD + m]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) { const float e = expf(S[n * LD + m] - mx); S[n * LD + m] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int n = lane; n < N; n += 32) {
+      const float a = S[n * LD + m] * inv;
+      S[n * LD + m] = a;
+      if (attn) attn[((size_t)b * M + m) * N + n] = a;
+    }
+    if (lane == 0) { rowmax[(size_t)b * M + m] = mx; rowsum[(size_t)b * M + m] = sum; }
+  }
+  __syncthreads();
+  if (P == nullptr) return;
+  for (int mb = 0; mb < M; mb += 32) {
+    for (int dd = threadIdx.x * 2; dd < D; dd += 2 * kThreads) {
+      float acc[32][2];
+      pool_phase<XT>(xb, S, N, D, M, mb, dd, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (mb + j < M)
+          *reinterpret_cast<float2*>(P + ((size_t)b * M + mb + j) * D + dd) = make_float2(acc[j][0], acc[j][1]);
+    }
+  }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(kThreads)
+pool_bwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, float scale, int N, int D, int M,
+                   const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                   const float* __restrict__ dP, const float* __restrict__ delta,
+                   float* __restrict__ dq_slots, int n_slots) {
+  extern __shared__ __align__(16) float S[];
+  const int b = blockIdx.x, LD = s_ld(M);
+  const XT* xb = x + (size_t)b * N * D;
+  for (int i = threadIdx.x; i < N * LD; i += kThreads) S[i] = 0.f;
+  __syncthreads();
+  logit_phase<XT, true>(xb, cls, dP + (size_t)b * M * D, scale, N, D, M, rowmax + (size_t)b * M,
+                        rowsum + (size_t)b * M, delta + (size_t)b * M, S);
+  __syncthreads();
+  float* slot = dq_slots + (size_t)(b % n_slots) * M * D;
+  for (int mb = 0; mb < M; mb += 32) {
+    for (int dd = threadIdx.x * 2; dd < D; dd += 2 * kThreads) {
+      float acc[32][2];
+      pool_phase<XT>(xb, S, N, D, M, mb, dd, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (mb + j < M) {
+          atomicAdd(slot + (size_t)(mb + j) * D + dd, acc[j][0]);
+          atomicAdd(slot + (size_t)(mb + j) * D + dd + 1, acc[j][1]);
+        }
+    }
+  }
+}
+
+__global__ void reduce_slots_kernel(const float* __restrict__ slots, int n_slots, size_t n, float scale,
+                                    float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < n_slots; ++k) s += slots[(size_t)k * n + i];
+  out[i] = s * scale;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) return EP_ERR_UNSUPPORTED;
+  if (bytes > 48 * 1024) EP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
+                float* P, float* rowmax, float* rowsum, float* attn, cudaStream_t s) {
+  if (M > 64) return EP_ERR_UNSUPPORTED;
+  const size_t smem = pool_v0_smem_bytes(N, M);
+  int rc;
+  if (x_dtype == EP_DTYPE_BF16) {
+    if ((rc = set_smem(pool_fwd_v0_kernel<__nv_bfloat16>, smem))) return rc;
+    pool_fwd_v0_kernel<__nv_bfloat16><<<B, kThreads, smem, s>>>((const __nv_bfloat16*)x, cls, scale, N, D, M, P,
+                                                                 rowmax, rowsum, attn);
+  } else {
+    if ((rc = set_smem(pool_fwd_v0_kernel<float>, smem))) return rc;
+    pool_fwd_v0_kernel<float><<<B, kThreads, smem, s>>>((const float*)x, cls, scale, N, D, M, P, rowmax, rowsum, attn);
+  }
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
+                const float* rowmax, const float* rowsum, const float* dP, const float* delta,
+                float* dq_slots, int n_slots, float* d_cls, cudaStream_t s) {
+  if (M > 64) return EP_ERR_UNSUPPORTED;
+  const size_t smem = pool_v0_smem_bytes(N, M);
+  const size_t n = (size_t)M * D;
+  EP_CUDA(cudaMemsetAsync(dq_slots, 0, n * n_slots * sizeof(float), s));
+  int rc;
+  if (x_dtype == EP_DTYPE_BF16) {
+    if ((rc = set_smem(pool_bwd_v0_kernel<__nv_bfloat16>, smem))) return rc;
+    pool_bwd_v0_kernel<__nv_bfloat16><<<B, kThreads, smem, s>>>((const __nv_bfloat16*)x, cls, scale, N, D, M, rowmax,
+                                                                 rowsum, dP, delta, dq_slots, n_slots);
+  } else {
+    if ((rc = set_smem(pool_bwd_v0_kernel<float>, smem))) return rc;
+    pool_bwd_v0_kernel<float><<<B, kThreads, smem, s>>>((const float*)x, cls, scale, N, D, M, rowmax, rowsum, dP, delta,
+                                                         dq_slots, n_slots);
+  }
+  EP_LAUNCH_CHECK();
+  reduce_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dq_slots, n_slots, n, scale, d_cls);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ep

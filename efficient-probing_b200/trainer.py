@@ -1,0 +1,309 @@
+"""EPHeadTrainer -- the reference's per-batch hot loop (engine_finetune.py:40-91) for an EP probe head
+trained on cached tokens, restructured for a 0.2 ms step:
+
+    tokens -> ep_fwd -> BatchNorm1d -> Linear -> CrossEntropy(+top-1) -> backward of all of it
+           -> gradient all-reduce (NCCL, flat buffer) -> LARS
+
+Every stage is one or two launches of libep_b200 on one stream; nothing synchronises with the host
+(the reference's per-step ``loss.item()``, ``acc.item()``, ``cuda.synchronize()`` and scalar all-reduce,
+engine_finetune.py:64,66,79-80,91, become device-side accumulators read when the caller asks), and the
+whole step is captured into a CUDA graph.  The parameters updated are the tensors of the
+``nn.Sequential(EfficientProbing, BatchNorm1d, Linear)`` passed in, in place, so ``head.state_dict()``
+stays the checkpoint format of util/misc.py:304-332.
+
+Multi-GPU (main_linprobe.py:581-583 DDP semantics): one process per GPU, batch sharded, BatchNorm
+statistics per GPU (no SyncBN), gradients summed with one NCCL all-reduce over a flat fp32 buffer
+``[fc.weight, fc.bias, v.weight, (v.bias), cls_token]`` and averaged inside the LARS kernel.  The first
+four become ready before the token-streaming half of the backward (ep_bwd_pool), so their all-reduce is
+issued on a communication stream underneath it; cls_token's 0.1-0.5 MB follows."""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib
+from .ep import EfficientProbing
+from .optim import lars_launch
+
+BN_EPS_DEFAULT = 1e-6
+
+
+class EPHeadTrainer:
+    def __init__(self, head: nn.Sequential, batch_size: int, num_tokens: int, *, lr: float = 0.1,
+                 weight_decay: float = 0.0, momentum: float = 0.9, trust_coefficient: float = 0.001,
+                 x_dtype: torch.dtype = torch.bfloat16, process_group=None, use_graph: bool = True,
+                 overlap_comm: bool = True):
+        pool, bn, fc = head[0], head[1], head[2]
+        if not isinstance(pool, EfficientProbing) or not isinstance(bn, nn.BatchNorm1d) or not isinstance(fc, nn.Linear):
+            raise TypeError("head must be Sequential(EfficientProbing, BatchNorm1d, Linear) (probe_heads.py:106)")
+        if bn.affine:
+            raise ValueError("the probe's BatchNorm1d is affine=False (probe_heads.py:110)")
+        self.head, self.pool, self.bn, self.fc = head, pool, bn, fc
+        self.lib = _lib.load()
+        dev = pool.cls_token.device
+        _lib.require_cuda(pool.cls_token, "head parameters")
+        _lib.check(self.lib.ep_device_check(), "ep_device_check")
+        self.dev = dev
+        self.B, self.N = int(batch_size), int(num_tokens)
+        self.D = pool.cls_token.shape[2]
+        self.M = pool.num_queries
+        self.d_out = pool.d_out
+        self.Dp = self.D // self.d_out
+        self.K = fc.out_features
+        self.x_dtype = x_dtype
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = use_graph
+        self.overlap_comm = overlap_comm and self.world > 1
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
+        # parameters, in the reference's parameters() order: cls_token, v.weight, [v.bias], fc.weight, fc.bias
+        self.params = [pool.cls_token, pool.v.weight] + ([pool.v.bias] if pool.v.bias is not None else []) + \
+                      [fc.weight, fc.bias]
+        for p in self.params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise TypeError("head parameters must be contiguous fp32")
+        self.trust = [p.ndim > 1 for p in self.params]                                   # util/lars.py:21
+        # flat gradient buffer: large, early-ready tensors first, cls_token last
+        sizes = {"fc_w": K * Dp, "fc_b": K, "v_w": Dp * D, "v_b": Dp if pool.v.bias is not None else 0, "cls": M * D}
+        self.flat_grad = torch.zeros(sum(sizes.values()), **f32)
+        off, self.g = 0, {}
+        for k, n in sizes.items():
+            self.g[k] = self.flat_grad[off:off + n]
+            off += n
+        self.n_early = off - sizes["cls"]
+        self.grads = [self.g["cls"], self.g["v_w"]] + ([self.g["v_b"]] if pool.v.bias is not None else []) + \
+                     [self.g["fc_w"], self.g["fc_b"]]
+        self.mus = [torch.zeros_like(p) for p in self.params]
+        # activations
+        self.x = torch.empty(B, N, D, dtype=x_dtype, device=dev)
+        self.targets = torch.empty(B, dtype=torch.int64, device=dev)
+        self.out = torch.empty(B, Dp, **f32)
+        self.rowmax = torch.empty(B, M, **f32)
+        self.rowsum = torch.empty(B, M, **f32)
+        self.P = torch.empty(B, M, D, **f32)
+        self.y = torch.empty(B, Dp, **f32)
+        self.save_mean = torch.empty(Dp, **f32)
+        self.save_invstd = torch.empty(Dp, **f32)
+        self.logits = torch.empty(B, K, **f32)
+        self.dlogits = torch.empty(B, K, **f32)
+        self.dy = torch.empty(B, Dp, **f32)
+        self.dout = torch.empty(B, Dp, **f32)
+        self.loss_sum = torch.zeros(1, **f32)            # running sum of per-step mean losses
+        self.step_loss = torch.zeros(1, **f32)           # mean loss of the last step
+        self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hyper = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world], **f32)
+        self.hyper_host = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world]).pin_memory()
+        self.lars_scratch = torch.empty(16, **f32)
+        self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
+        self._cx, self._ct = self.x, self.targets           # the batch the next launch sequence reads
+        self._registered = {}                               # (x ptr, targets ptr) -> (x, targets) kept alive
+        self.graphs = {}                                    # (x ptr, targets ptr) -> captured step
+        self.steps = 0
+        self.launches_per_step = None
+        # pinned staging for the host-buffer API
+        self._hx = self._ht = self._hloss = None
+
+    # ------------------------------------------------------------------ one step, stream-ordered
+    def _forward(self, training: bool):
+        lib, s = self.lib, _lib.stream_ptr(self.dev)
+        B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
+        pool, bn, fc = self.pool, self.bn, self.fc
+        _lib.check(lib.ep_fwd(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
+                              pool.v.weight.data_ptr(), _lib.ptr(pool.v.bias), float(pool.scale), B, N, D, M, self.d_out,
+                              self.out.data_ptr(), self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.P.data_ptr(),
+                              None, self.ws.data_ptr(), self.ws.numel(), s), "ep_fwd")
+        _lib.check(lib.ep_bn_fwd(self.out.data_ptr(), B, Dp, float(bn.eps), float(bn.momentum), int(training),
+                                 bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                 bn.num_batches_tracked.data_ptr(), self.y.data_ptr(), self.save_mean.data_ptr(),
+                                 self.save_invstd.data_ptr(), s), "ep_bn_fwd")
+        _lib.check(lib.ep_linear_fwd(self.y.data_ptr(), fc.weight.data_ptr(), fc.bias.data_ptr(), B, Dp, K,
+                                     self.logits.data_ptr(), s), "ep_linear_fwd")
+
+    def _step_body(self):
+        lib, s = self.lib, _lib.stream_ptr(self.dev)
+        B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
+        pool, fc = self.pool, self.fc
+        self._forward(training=True)
+        self.step_loss.zero_()
+        _lib.check(lib.ep_ce_fwd_bwd(self.logits.data_ptr(), self._ct.data_ptr(), B, K, 1.0 / B, 1.0 / B,
+                                     self.step_loss.data_ptr(), self.dlogits.data_ptr(), self.correct.data_ptr(), s),
+                   "ep_ce_fwd_bwd")
+        _lib.check(lib.ep_linear_bwd(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
+                                     self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), self.dy.data_ptr(), s),
+                   "ep_linear_bwd")
+        _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
+                                 self.dout.data_ptr(), s), "ep_bn_bwd")
+        d_vb = self.g["v_b"].data_ptr() if pool.v.bias is not None else None
+        _lib.check(lib.ep_bwd_proj(self.dout.data_ptr(), self.P.data_ptr(), pool.v.weight.data_ptr(), B, N, D, M,
+                                   self.d_out, self.g["v_w"].data_ptr(), d_vb, self.ws.data_ptr(), self.ws.numel(), s),
+                   "ep_bwd_proj")
+        if self.overlap_comm:
+            # the first n_early floats are final: reduce them underneath the token-streaming half
+            cur = torch.cuda.current_stream(self.dev)
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.flat_grad[:self.n_early], group=self.group)
+        _lib.check(lib.ep_bwd_pool(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
+                                   float(pool.scale), B, N, D, M, self.d_out, self.rowmax.data_ptr(),
+                                   self.rowsum.data_ptr(), self.g["cls"].data_ptr(), self.ws.data_ptr(),
+                                   self.ws.numel(), s), "ep_bwd_pool")
+        if self.world > 1:
+            if self.overlap_comm:
+                dist.all_reduce(self.flat_grad[self.n_early:], group=self.group)
+                torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+            else:
+                dist.all_reduce(self.flat_grad, group=self.group)
+        lars_launch(self.params, self.grads, self.mus, self.trust, self.hyper, self.lars_scratch)
+        self.loss_sum.add_(self.step_loss)
+
+    def _run(self):
+        if not self.use_graph:
+            if self.launches_per_step is None:
+                n0 = self.lib.ep_launch_count()
+                self._step_body()
+                self.launches_per_step = int(self.lib.ep_launch_count() - n0)
+            else:
+                self._step_body()
+            return
+        key = (self._cx.data_ptr(), self._ct.data_ptr())
+        graph = self.graphs.get(key)
+        if graph is None:
+            snap = self._snapshot()
+            if not self.graphs:
+                # one eager step on a side stream first (lazy module loading, NCCL communicator set-up)
+                side = torch.cuda.Stream(device=self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(side):
+                    n0 = self.lib.ep_launch_count()
+                    self._step_body()
+                    self.launches_per_step = int(self.lib.ep_launch_count() - n0)
+                torch.cuda.current_stream(self.dev).wait_stream(side)
+                torch.cuda.synchronize(self.dev)
+                self._restore(snap)
+            graph = torch.cuda.CUDAGraph()
+            mode = "thread_local" if self.world > 1 else "global"
+            with torch.cuda.graph(graph, capture_error_mode=mode):
+                self._step_body()
+            self.graphs[key] = graph
+        graph.replay()
+
+    def _snapshot(self):
+        bn = self.bn
+        return ([p.detach().clone() for p in self.params], [m.clone() for m in self.mus], bn.running_mean.clone(),
+                bn.running_var.clone(), bn.num_batches_tracked.clone(), self.loss_sum.clone(), self.correct.clone())
+
+    def _restore(self, snap):
+        ps, ms, rm, rv, nbt, ls, cr = snap
+        with torch.no_grad():
+            for p, q in zip(self.params, ps):
+                p.copy_(q)
+            for m, q in zip(self.mus, ms):
+                m.copy_(q)
+            self.bn.running_mean.copy_(rm)
+            self.bn.running_var.copy_(rv)
+            self.bn.num_batches_tracked.copy_(nbt)
+            self.loss_sum.copy_(ls)
+            self.correct.copy_(cr)
+
+    # ------------------------------------------------------------------ public API
+    def set_lr(self, lr: float, weight_decay: Optional[float] = None):
+        """Host scalar from the schedule (util/lr_sched.py) -> device, without a sync."""
+        self.hyper_host[0] = lr
+        if weight_decay is not None:
+            self.hyper_host[1] = weight_decay
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    @torch.no_grad()
+    def train_step(self, x: torch.Tensor, targets: torch.Tensor, lr: Optional[float] = None):
+        """One optimisation step on a device-resident batch: x (B, N, D), targets (B,) int64.
+        Returns nothing; read ``mean_loss()`` / ``top1()`` when needed."""
+        if x.shape != self.x.shape or x.dtype != self.x_dtype:
+            raise ValueError(f"x must be {tuple(self.x.shape)} {self.x_dtype}, got {tuple(x.shape)} {x.dtype}")
+        if lr is not None:
+            self.set_lr(lr)
+        key = (x.data_ptr(), targets.data_ptr())
+        if key in self._registered:
+            self._cx, self._ct = self._registered[key]        # resident batch: read it where it lies
+        else:
+            self._cx, self._ct = self.x, self.targets
+            if x.data_ptr() != self.x.data_ptr():
+                self.x.copy_(x, non_blocking=True)
+            if targets.data_ptr() != self.targets.data_ptr():
+                self.targets.copy_(targets, non_blocking=True)
+        self._run()
+        self.steps += 1
+
+    def register_batch(self, x: torch.Tensor, targets: torch.Tensor):
+        """Declare a device-resident batch (e.g. one slot of a token-cache pool) that train_step may read in
+        place, without the staging copy; each registered batch gets its own captured graph."""
+        if x.shape != self.x.shape or x.dtype != self.x_dtype or not x.is_contiguous() or x.device != self.dev:
+            raise ValueError("registered batch must match the trainer's (B, N, D), dtype and device")
+        if targets.dtype != torch.int64 or targets.shape != (self.B,):
+            raise ValueError("targets must be (B,) int64")
+        self._registered[(x.data_ptr(), targets.data_ptr())] = (x, targets)
+
+    @torch.no_grad()
+    def train_step_host(self, x_host: torch.Tensor, targets_host: torch.Tensor, lr: Optional[float] = None) -> float:
+        """End-to-end step from HOST buffers: pinned-memory H2D copy of tokens and labels, the step, and a
+        D2H read of the step's mean loss (the reference loop's samples.to(device) ... loss.item())."""
+        if not x_host.is_pinned():
+            if self._hx is None:
+                self._hx = torch.empty(self.x.shape, dtype=self.x_dtype).pin_memory()
+                self._ht = torch.empty(self.B, dtype=torch.int64).pin_memory()
+            self._hx.copy_(x_host)
+            self._ht.copy_(targets_host)
+            x_host, targets_host = self._hx, self._ht
+        if self._hloss is None:
+            self._hloss = torch.empty(1, dtype=torch.float32).pin_memory()
+        if lr is not None:
+            self.set_lr(lr)
+        self._cx, self._ct = self.x, self.targets
+        self.x.copy_(x_host, non_blocking=True)
+        self.targets.copy_(targets_host, non_blocking=True)
+        self._run()
+        self.steps += 1
+        self._hloss.copy_(self.step_loss, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return float(self._hloss[0])
+
+    @torch.no_grad()
+    def eval_logits(self, x: torch.Tensor) -> torch.Tensor:
+        """model.eval() forward (BatchNorm on running statistics), engine_finetune.py:106-166."""
+        self._cx = self.x
+        self.x.copy_(x, non_blocking=True)
+        self._forward(training=False)
+        return self.logits.clone()
+
+    def mean_loss(self) -> float:
+        """Mean of the per-step losses since the last reset (one D2H sync, on demand)."""
+        v = float(self.loss_sum.item()) / max(self.steps, 1)
+        return v
+
+    def top1(self) -> float:
+        return float(self.correct.item()) / max(self.steps * self.B, 1)
+
+    def reset_meters(self):
+        self.loss_sum.zero_()
+        self.correct.zero_()
+        self.steps = 0
+
+    def optimizer_state_dict(self):
+        """torch.optim-style state for util/misc.py:322 checkpoints: state[i]['mu'] in parameters() order."""
+        return {"state": {i: {"mu": m.clone()} for i, m in enumerate(self.mus)},
+                "param_groups": [{"lr": float(self.hyper_host[0]), "weight_decay": float(self.hyper_host[1]),
+                                  "momentum": float(self.hyper_host[2]), "trust_coefficient": float(self.hyper_host[3]),
+                                  "params": list(range(len(self.params)))}]}
+
+    def load_optimizer_state_dict(self, sd):
+        for i, m in enumerate(self.mus):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is not None and "mu" in st:
+                m.copy_(st["mu"].to(m.device))
+        g = sd["param_groups"][0]
+        self.hyper_host[0], self.hyper_host[1] = g["lr"], g["weight_decay"]
+        self.hyper_host[2], self.hyper_host[3] = g.get("momentum", 0.9), g.get("trust_coefficient", 0.001)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)

@@ -1,0 +1,133 @@
+/* ep_b200.h -- C ABI of libep_b200.so, the sm_100a implementation of the EP probe-head hot path.
+ *
+ * Every entry point replaces a piece of the reference's PyTorch-eager path (paths relative to
+ * billpsomas/efficient-probing); the Python host side (efficient-probing_b200/) binds them with
+ * ctypes, INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named *_host;
+ *   - the library never allocates, frees or retains device memory: outputs and workspace are
+ *     caller-owned (PyTorch caching allocator on the reference side);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and is CUDA-graph capturable; no global mutable state, re-entrant;
+ *   - return 0 on success, a NEGATIVE ep_status for rejected arguments, a POSITIVE value for a
+ *     cudaError_t raised by a launch.  There is no CPU fallback of any kind.
+ *   - tensors are contiguous row-major; token tensors x are (B, N, D) bf16 (EP_DTYPE_BF16, the fast
+ *     path) or fp32 (EP_DTYPE_F32, converted on load); parameters, statistics, gradients fp32.
+ */
+#ifndef EP_B200_H_
+#define EP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EP_ABI_VERSION 1
+
+#define EP_DTYPE_BF16 0
+#define EP_DTYPE_F32  1
+
+typedef enum {
+  EP_OK = 0,
+  EP_ERR_NULL = -1,        /* a required pointer is NULL                                   */
+  EP_ERR_SHAPE = -2,       /* B,N,D,M,d_out <= 0 or D % (d_out*M) != 0 (ep.py:40 reshape)   */
+  EP_ERR_ALIGN = -3,       /* D % 8 != 0 (128-bit token loads) or misaligned pointer        */
+  EP_ERR_DTYPE = -4,       /* x_dtype not EP_DTYPE_BF16 / EP_DTYPE_F32                      */
+  EP_ERR_WORKSPACE = -5,   /* workspace smaller than ep_workspace_bytes()                   */
+  EP_ERR_UNSUPPORTED = -6, /* shape outside what the kernels cover (e.g. N*M too large)     */
+  EP_ERR_DEVICE = -7       /* current device is not compute capability 10.x                 */
+} ep_status;
+
+int ep_abi_version(void);
+const char* ep_strerror(int code);
+/* 0 when the current CUDA device is sm_100-class, EP_ERR_DEVICE otherwise. */
+int ep_device_check(void);
+/* Select the pooling kernel family: 0 = automatic (tcgen05 kernels where the shape allows, else the
+ * general kernels), 1 = force the general CUDA-core kernels, 2 = force tcgen05 (error if unsupported). */
+int ep_set_kernel_mode(int mode);
+/* Which family the last ep_fwd/ep_bwd call on this thread used (1 = general, 2 = tcgen05). */
+int ep_last_kernel_family(void);
+/* Number of kernels this library has launched in this process (host-side count; launches replayed by a
+ * CUDA graph are not seen here -- count the captured step once and multiply). */
+unsigned long long ep_launch_count(void);
+
+/* Bytes of scratch ep_fwd / ep_bwd / ep_attention_maps need for this shape (max over the three). */
+size_t ep_workspace_bytes(int B, int N, int D, int M, int d_out);
+
+/* EfficientProbing.forward -- poolings/ep.py:28-47 (num_heads == 1).
+ *   S[b,m,n] = scale * cls_token[m] . x[b,n];  A = softmax_n(S);  P[b,m] = sum_n A[b,m,n] x[b,n];
+ *   out[b, m*c:(m+1)*c] = v_w[m*c:(m+1)*c] @ P[b,m] (+ v_b),  c = D / (d_out*M).
+ * Outputs: out (B, D/d_out); saved for backward: rowmax, rowsum (B, M) -- the shift and the
+ * normaliser of the softmax (A = exp(S - rowmax) / rowsum) -- and P (B, M, D).
+ * attn (B, M, N) is written when non-NULL (the attention maps of tools/ep_attention_maps.py:51-58). */
+int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
+           float scale, int B, int N, int D, int M, int d_out,
+           float* out, float* rowmax, float* rowsum, float* P, float* attn,
+           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of ep_fwd (replaces autograd through ep.py:35-45; engine_finetune.py:73 -> misc.py:267).
+ * g_out = dL/d out (B, D/d_out).  Writes d_cls_token (M, D), d_v_w (D/d_out, D), d_v_b (D/d_out,
+ * nullable).  The frozen-backbone path needs no dL/dx (main_linprobe.py:393-400). */
+int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale,
+           int B, int N, int D, int M, int d_out,
+           const float* rowmax, const float* rowsum, const float* P, const float* g_out,
+           float* d_cls_token, float* d_v_w, float* d_v_b,
+           void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two halves of ep_bwd, for callers that overlap the gradient all-reduce with the token-streaming
+ * half (the DDP bucket overlap of main_linprobe.py:581-583, done explicitly):
+ *   ep_bwd_proj : needs only g_out and the saved P -- writes d_v_w, d_v_b (99% of the EP gradient bytes)
+ *                 and leaves dP = g_out . v_w and delta = dP . P in the workspace;
+ *   ep_bwd_pool : streams x once, recomputes A, writes d_cls_token.  Must follow ep_bwd_proj on the
+ *                 same stream with the same workspace. */
+int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int B, int N, int D, int M, int d_out,
+                float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes, void* stream);
+int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M, int d_out,
+                const float* rowmax, const float* rowsum, float* d_cls_token,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* tools/ep_attention_maps.py:51-58 for a batch: attn[b] = softmax(scale * cls_token @ x[b]^T), (B, M, N). */
+int ep_attention_maps(const void* x, int x_dtype, const float* cls_token, float scale,
+                      int B, int N, int D, int M, float* attn,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* nn.BatchNorm1d(F, affine=False, eps) -- probe_heads.py:109-110.
+ * training != 0: batch statistics (biased variance), running stats updated with `momentum`
+ * (unbiased variance), *num_batches_tracked += 1; save_mean / save_invstd (F,) kept for backward.
+ * training == 0: y = (h - running_mean) / sqrt(running_var + eps). */
+int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum, int training,
+              float* running_mean, float* running_var, long long* num_batches_tracked,
+              float* y, float* save_mean, float* save_invstd, void* stream);
+/* dh = invstd * (dy - mean_b(dy) - y * mean_b(dy*y)). */
+int ep_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, void* stream);
+
+/* nn.Linear(F, K, bias=True) -- probe_heads.py:76.  logits = y @ W^T + b. */
+int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits, void* stream);
+/* dW = dlogits^T @ y (K, F); db = sum_b dlogits (K,); dy = dlogits @ W (B, F).  Any output may be NULL. */
+int ep_linear_bwd(const float* dlogits, const float* y, const float* W, int B, int F, int K,
+                  float* dW, float* db, float* dy, void* stream);
+
+/* nn.CrossEntropyLoss() (mean) forward + backward in one pass -- main_linprobe.py:589, engine_finetune.py:62.
+ * loss_sum[0] += sum_b nll_b * loss_scale  (caller zeroes it; loss_scale = 1/B gives the mean);
+ * dlogits = (softmax(logits) - onehot) * grad_scale  (grad_scale = 1/B for the mean loss);
+ * correct[0] += #(argmax == target) when non-NULL (engine_finetune.py:63 top-1). */
+int ep_ce_fwd_bwd(const float* logits, const long long* targets, int B, int K, float loss_scale, float grad_scale,
+                  float* loss_sum, float* dlogits, int* correct, void* stream);
+
+/* util/lars.py:13-37 for up to EP_LARS_MAX_TENSORS tensors in one call (pointer tables are HOST arrays
+ * of device pointers).  hyper is a DEVICE array {lr, weight_decay, momentum, trust_coefficient, grad_scale}
+ * so a captured graph can be replayed with a new learning rate; grad_scale (1/world_size after a
+ * sum all-reduce) multiplies every gradient first.  apply_trust_host[i] != 0 for tensors with
+ * ndim > 1 (lars.py:21).  scratch: 2*n floats. */
+#define EP_LARS_MAX_TENSORS 8
+int ep_lars_step(int n, float* const* params_host, const float* const* grads_host, float* const* mus_host,
+                 const long long* numels_host, const int* apply_trust_host, const float* hyper,
+                 float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EP_B200_H_ */

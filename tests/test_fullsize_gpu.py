@@ -1,0 +1,91 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties (the CPU oracle cannot
+run these shapes in seconds), plus the fixed 10k-sample top-1 agreement against the oracle."""
+import pytest
+import torch
+
+import efficient_probing_b200 as E
+from oracle import ep_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _tokens(B, N, D, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(B, N, D, device=DEV, generator=g).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,N,D,M", [(1024, 257, 1024, 32), (1024, 257, 1024, 8), (256, 730, 1664, 32)])
+def test_fullsize_properties(B, N, D, M):
+    torch.manual_seed(0)
+    pool = E.EfficientProbing(D, num_queries=M).to(DEV)
+    with torch.no_grad():
+        pool.cls_token.mul_(20.0)                      # non-trivial attention
+    x = _tokens(B, N, D, 1234)
+    out = pool(x)
+    attn = pool.attention_maps(x)
+    # (1) attention rows are distributions
+    assert float((attn.sum(-1) - 1).abs().max()) < 1e-4 and float(attn.min()) >= 0
+    # (2) token-permutation invariance of the pooled output
+    perm = torch.randperm(N, device=DEV)
+    out_p = pool(x[:, perm].contiguous())
+    assert O.rel_err(out_p.cpu(), out.cpu()) < 1e-3
+    # (3) samples are independent: any sub-batch gives the same rows
+    idx = torch.tensor([0, 1, B // 2, B - 1], device=DEV)
+    out_s = pool(x[idx].contiguous())
+    assert O.rel_err(out_s.cpu(), out[idx].cpu()) < 1e-3
+    # (4) a sub-batch agrees with the CPU oracle
+    ref = O.ep_forward(x[idx].cpu().double(), pool.cls_token.detach().cpu().double(),
+                       pool.v.weight.detach().cpu().double(), None, pool.scale, M, 1)
+    assert O.rel_err(out_s.cpu(), ref) < 1e-3
+    # (5) constant token field: attention sums to one, so the pooled token is the field itself
+    v = torch.randn(D, device=DEV).to(torch.bfloat16)
+    xc = v.expand(4, N, D).contiguous()
+    ref_c = torch.nn.functional.linear(v.float(), pool.v.weight)
+    assert O.rel_err(pool(xc).cpu(), ref_c.expand(4, -1).cpu()) < 1e-3
+    # (6) directional derivative of a scalar loss w.r.t. the queries and the projection
+    g = torch.randn_like(out)
+    pool.zero_grad()
+    (pool(x) * g).sum().backward()
+    for prm in (pool.cls_token, pool.v.weight):
+        u = torch.randn_like(prm)
+        u /= u.norm()
+        eps = 1e-2 * float(prm.norm())
+        with torch.no_grad():
+            prm.add_(eps * u)
+            lp = float((pool(x).double() * g.double()).sum())
+            prm.sub_(2 * eps * u)
+            lm = float((pool(x).double() * g.double()).sum())
+            prm.add_(eps * u)
+        fd = (lp - lm) / (2 * eps)
+        an = float((prm.grad.double() * u.double()).sum())
+        assert abs(fd - an) <= 2e-2 * max(abs(fd), abs(an)) + 1e-3, (fd, an)
+
+
+def test_top1_identical_on_10k_samples():
+    """BASELINE.json: identical top-1 predictions on a fixed 10k-sample set (config-1 token shape)."""
+    N, D, M, K, B = 197, 768, 8, 1000, 500
+    torch.manual_seed(0)
+    head = E.make_ep_head(D, M, K).to(DEV)
+    tr = E.EPHeadTrainer(head, B, N, lr=2.0, use_graph=True)
+    # a short training run on class-shifted synthetic tokens so that predictions have real margins
+    for it in range(30):
+        y = O.synthetic_labels(B, K, seed=100 + it)
+        x = O.synthetic_tokens(B, N, D, seed=200 + it, class_shift=y)
+        tr.train_step(x.to(DEV), y.to(DEV))
+    torch.cuda.synchronize()
+    p = O.EPParams(head[0].cls_token.detach().cpu(), head[0].v.weight.detach().cpu(), None,
+                   head[1].running_mean.cpu(), head[1].running_var.cpu(), int(head[1].num_batches_tracked),
+                   head[2].weight.detach().cpu(), head[2].bias.detach().cpu(), M, 1, head[0].scale)
+    agree = total = 0
+    worst = 0.0
+    for chunk in range(20):                            # 20 x 500 = 10 000 fixed samples
+        y = O.synthetic_labels(B, K, seed=5000 + chunk)
+        x = O.synthetic_tokens(B, N, D, seed=6000 + chunk, class_shift=y)
+        got = tr.eval_logits(x.to(DEV)).cpu()
+        ref = O.head_forward(p, x.float(), train=False)["logits"]
+        worst = max(worst, O.rel_err(got, ref))
+        agree += int((got.argmax(1) == ref.argmax(1)).sum())
+        total += B
+    assert worst < 1e-3, worst
+    assert agree == total == 10000, (agree, total)

@@ -1,0 +1,170 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in module and the fused trainer)
+against the committed outputs of the reference (tests/golden) and against the CPU oracle on seeded
+inputs.  Tolerances are BASELINE.json's: attention maps and logits 1e-3, parameter gradients 2e-3
+(relative L2 error, fp32 accumulate)."""
+import pytest
+import torch
+from torch import nn
+
+import efficient_probing_b200 as E
+from oracle import ep_oracle as O
+from conftest import Golden, GOLDEN_CASES
+
+pytestmark = pytest.mark.gpu
+TOL_FWD, TOL_GRAD = 1e-3, 2e-3
+DEV = "cuda:0"
+
+
+def head_from_params(p: O.EPParams, K):
+    D = p.cls_token.shape[2]
+    h = E.make_ep_head(D, p.num_queries, K, d_out=p.d_out, qkv_bias=p.v_bias is not None)
+    sd = {"0.cls_token": p.cls_token, "0.v.weight": p.v_weight, "1.running_mean": p.running_mean,
+          "1.running_var": p.running_var, "1.num_batches_tracked": torch.tensor(p.num_batches_tracked),
+          "2.weight": p.fc_weight, "2.bias": p.fc_bias}
+    if p.v_bias is not None:
+        sd["0.v.bias"] = p.v_bias
+    h.load_state_dict(sd)                              # reference checkpoint keys load unchanged
+    return h.to(DEV)
+
+
+def close(got, ref, tol, what):
+    ref = ref.to(got.device)
+    err = (got.double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30)
+    if ref.double().norm() < 1e-12:                    # identically-zero reference (bias under BatchNorm)
+        assert got.double().norm() < 1e-6, what
+        return
+    assert float(err) < tol, f"{what}: rel err {float(err):.3e} > {tol}"
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float32])
+def test_module_forward_backward_vs_reference_golden(name, xdt):
+    g = Golden(name)
+    head = head_from_params(g.params(), g.meta["K"])
+    head.train()
+    x = g.t("x").to(DEV).to(xdt)                       # fixture tokens are bf16-representable
+    y = g.t("targets").to(DEV)
+    pooled = head[0](x)
+    logits = head[2](head[1](pooled))
+    loss = nn.CrossEntropyLoss()(logits, y)
+    loss.backward()
+    close(pooled, g.t("f64.out"), TOL_FWD, "out")
+    close(logits, g.t("f64.logits"), TOL_FWD, "logits")
+    close(head[0].attention_maps(x), g.t("f64.attn"), TOL_FWD, "attn")
+    close(E.ep_attention(x[0], head[0].cls_token[0]), g.t("f64.attn")[0], TOL_FWD, "ep_attention")
+    assert abs(float(loss) - float(g.z["f64.loss"])) < 1e-3 * abs(float(g.z["f64.loss"]))
+    for k, p in head.named_parameters():
+        close(p.grad, g.t("f64.grad." + k), TOL_GRAD, "grad " + k)
+    close(head[1].running_mean, g.t("f64.running_mean"), TOL_FWD, "running_mean")
+    close(head[1].running_var, g.t("f64.running_var"), TOL_FWD, "running_var")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_two_lars_steps_vs_reference_golden(name, graph):
+    g = Golden(name)
+    m = g.meta
+    head = head_from_params(g.params(), m["K"])
+    x = g.t("x").to(DEV).to(torch.bfloat16)
+    y = g.t("targets").to(DEV)
+    tr = E.EPHeadTrainer(head, m["B"], m["N"], lr=m["lr"], weight_decay=m["weight_decay"], use_graph=graph)
+    tr.train_step(x, y)
+    torch.cuda.synchronize()
+    assert abs(float(tr.step_loss) - float(g.z["f64.loss"])) < 1e-3 * abs(float(g.z["f64.loss"]))
+    close(tr.logits, g.t("f64.logits"), TOL_FWD, "logits")
+    for k, grad in zip([n for n, _ in head.named_parameters()], tr.grads):
+        close(grad.reshape(-1), g.t("f64.grad." + k).reshape(-1), TOL_GRAD, "grad " + k)
+    tr.train_step(x, y)
+    torch.cuda.synchronize()
+    assert abs(float(tr.step_loss) - float(g.z["f64.loss_step2"])) < 1e-3 * abs(float(g.z["f64.loss_step2"]))
+    for k, p in head.named_parameters():
+        close(p, g.t("f64.after2." + k), 1e-3, "param after 2 LARS steps " + k)
+    assert int(head[1].num_batches_tracked) == 2
+    # eval-mode logits on running statistics (engine_finetune.py:106-166)
+    head2 = head_from_params(g.params(), m["K"])
+    head2[1].running_mean.copy_(g.t("f64.running_mean").float())
+    head2[1].running_var.copy_(g.t("f64.running_var").float())
+    tr2 = E.EPHeadTrainer(head2, m["B"], m["N"], use_graph=False)
+    close(tr2.eval_logits(x), g.t("f64.eval_logits"), TOL_FWD, "eval logits")
+
+
+CASES = [  # B, N, D, M, K, d_out, bias, spread, q_gain
+    (8, 197, 768, 8, 1000, 1, False, 1.0, 1.0),        # BASELINE config 1 shape (smaller batch)
+    (4, 257, 1024, 32, 1000, 1, False, 1.0, 25.0),     # config 2 shape, sharpened attention
+    (3, 256, 1152, 32, 100, 1, False, 1.0, 1.0),       # config 3 shape
+    (2, 730, 1664, 32, 64, 1, False, 1.0, 10.0),       # config 4 shape (long N)
+    (2, 201, 4096, 32, 32, 1, False, 1.0, 10.0),       # config 5 shape (wide D)
+    (5, 50, 384, 12, 10, 2, True, 8.0, 20.0),          # d_out=2, bias, M not a power of two, logits ~ +-30
+    (1, 1, 64, 8, 4, 1, False, 1.0, 1.0),              # single token: attention == 1
+    (3, 1370, 768, 8, 10, 1, False, 1.0, 5.0),         # Franca@518 token count
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_N%d_D%d_M%d_K%d_do%d_b%d" % c[:7])
+def test_seeded_shapes_vs_oracle(case):
+    B, N, D, M, K, d_out, bias, spread, q_gain = case
+    p = O.build_head(D, M, K, d_out=d_out, qkv_bias=bias, seed=0)
+    p.cls_token = p.cls_token * q_gain
+    x = O.synthetic_tokens(B, N, D, seed=1234, spread=spread)
+    y = O.synthetic_labels(B, K)
+    if B > 1:
+        ref = O.head_loss_and_grads(p, x.float(), y, dtype=torch.float64)
+    else:
+        o, a = O.ep_forward(x.double(), p.cls_token.double(), p.v_weight.double(), None, p.scale, M, d_out, True)
+        ref = {"out": o, "attn": a}
+    head = head_from_params(p, K)
+    head.train()
+    xg, yg = x.to(DEV), y.to(DEV)
+    pooled = head[0](xg)
+    close(pooled, ref["out"], TOL_FWD, "out")
+    close(head[0].attention_maps(xg), ref["attn"], TOL_FWD, "attn")
+    if B == 1:                                         # BatchNorm1d cannot train on one sample (torch raises too)
+        return
+    logits = head[2](head[1](pooled))
+    nn.CrossEntropyLoss()(logits, yg).backward()
+    if B > 1:
+        close(logits, ref["logits"], TOL_FWD, "logits")
+        for k, prm in head.named_parameters():
+            close(prm.grad, ref["grad." + k], TOL_GRAD, "grad " + k)
+    # the fused trainer computes the same step
+    head_t = head_from_params(p, K)
+    tr = E.EPHeadTrainer(head_t, B, N, lr=0.0, use_graph=False)
+    tr.train_step(xg, yg)
+    if B > 1:
+        close(tr.logits, ref["logits"], TOL_FWD, "trainer logits")
+        for k, grad in zip([n for n, _ in head_t.named_parameters()], tr.grads):
+            close(grad.reshape(-1), ref["grad." + k].reshape(-1), TOL_GRAD, "trainer grad " + k)
+
+
+def test_lars_optimizer_matches_oracle():
+    torch.manual_seed(3)
+    shapes = [(1, 8, 64), (64, 64), (64,), (10, 64), (10,)]
+    ps = [torch.randn(s) for s in shapes]
+    gs = [torch.randn(s) * 0.1 for s in shapes]
+    params = [nn.Parameter(p.clone().to(DEV)) for p in ps]
+    opt = E.LARS(params, lr=0.3, weight_decay=1e-2)
+    mus = [torch.zeros_like(p) for p in ps]
+    cur = [p.double() for p in ps]
+    mus = [m.double() for m in mus]
+    for it in range(3):
+        for p, g in zip(params, gs):
+            p.grad = (g * (it + 1)).to(DEV)
+        opt.step()
+        cur, mus = O.lars_step(cur, [g.double() * (it + 1) for g in gs], mus, lr=0.3, weight_decay=1e-2)
+    for p, c in zip(params, cur):
+        close(p.detach(), c, 1e-5, "lars")
+    sd = opt.state_dict()
+    assert set(sd["state"][0].keys()) == {"mu"}           # same optimizer-state layout as util/lars.py
+
+
+def test_errors_are_loud():
+    head = E.make_ep_head(64, 8, 10).to(DEV)
+    with pytest.raises(TypeError):
+        head[0](torch.randn(2, 5, 64, device=DEV, dtype=torch.float16))
+    with pytest.raises(ValueError):
+        head[0](torch.zeros(2, 5, 72, device=DEV))        # cls_token is (1, 8, 64)
+    x = torch.randn(2, 5, 64, device=DEV, requires_grad=True)
+    out = head[0](x)
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()
+    assert E._lib.load().ep_device_check() == 0
