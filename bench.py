@@ -273,13 +273,13 @@ def main():
     def fwd(i):
         x = pool_x[i % args.pool]
         E._lib.check(lib.ep_fwd(x.data_ptr(), xt, pool_mod.cls_token.data_ptr(), pool_mod.v.weight.data_ptr(), None,
-                                float(pool_mod.scale), B, N, D, M, 1, tr.out.data_ptr(), tr.rowmax.data_ptr(),
+                                float(pool_mod.scale), B, N, D, M, 1, tr.out.data_ptr(), tr.S.data_ptr(), tr.rowmax.data_ptr(),
                                 tr.rowsum.data_ptr(), tr.P.data_ptr(), None, tr.ws.data_ptr(), tr.ws.numel(), s), "ep_fwd")
 
     def bwd_pool(i):
         x = pool_x[i % args.pool]
         E._lib.check(lib.ep_bwd_pool(x.data_ptr(), xt, pool_mod.cls_token.data_ptr(), float(pool_mod.scale), B, N, D, M,
-                                     1, tr.rowmax.data_ptr(), tr.rowsum.data_ptr(), tr.g["cls"].data_ptr(),
+                                     1, tr.S.data_ptr(), tr.rowmax.data_ptr(), tr.rowsum.data_ptr(), tr.g["cls"].data_ptr(),
                                      tr.ws.data_ptr(), tr.ws.numel(), s), "ep_bwd_pool")
 
     def proj(i):                                                  # ep_fwd minus its streaming kernel
@@ -295,7 +295,7 @@ def main():
 
     def fwd_small(i):
         E._lib.check(lib.ep_fwd(x1.data_ptr(), xt, pool_mod.cls_token.data_ptr(), pool_mod.v.weight.data_ptr(), None,
-                                float(pool_mod.scale), B, 1, D, M, 1, tr.out.data_ptr(), tr.rowmax.data_ptr(),
+                                float(pool_mod.scale), B, 1, D, M, 1, tr.out.data_ptr(), tr.S.data_ptr(), tr.rowmax.data_ptr(),
                                 tr.rowsum.data_ptr(), tr.P.data_ptr(), None, ws1.data_ptr(), ws1.numel(), s), "ep_fwd")
     t_proj = time_kernel(fwd_small, 10, noflush)
     t_fwd = max(t_fwd_all - t_proj, 1e-6)

@@ -24,13 +24,14 @@ _SIGNATURES = {
     "ep_set_kernel_mode": (c_int, [c_int]),
     "ep_last_kernel_family": (c_int, []),
     "ep_launch_count": (ctypes.c_ulonglong, []),
+    "ep_kernel_family_for": (c_int, [c_int] * 5),
     "ep_workspace_bytes": (c_size_t, [c_int] * 5),
     "ep_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 5 +
-               [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),
+               [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ep_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float] + [c_int] * 5 +
-               [c_void_p] * 4 + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+               [c_void_p] * 5 + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "ep_bwd_proj": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "ep_bwd_pool": (c_int, [c_void_p, c_int, c_void_p, c_float] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p,
+    "ep_bwd_pool": (c_int, [c_void_p, c_int, c_void_p, c_float] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_void_p,
                                                                                    c_void_p, c_size_t, c_void_p]),
     "ep_attention_maps": (c_int, [c_void_p, c_int, c_void_p, c_float] + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ep_bn_fwd": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int] + [c_void_p] * 7),

@@ -38,6 +38,10 @@ extern "C" int ep_set_kernel_mode(int mode) {
   return 0;
 }
 extern "C" int ep_last_kernel_family(void) { return t_last_family; }
+extern "C" int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M) {
+  if (g_kernel_mode == 1) return 1;
+  return sm100_supported(x_dtype, B, N, D, M) ? 2 : (g_kernel_mode == 2 ? 0 : 1);
+}
 extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count; }
 
 namespace {
@@ -79,21 +83,21 @@ extern "C" size_t ep_workspace_bytes(int B, int N, int D, int M, int d_out) {
 }
 
 extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
-                      float scale, int B, int N, int D, int M, int d_out, float* out, float* rowmax, float* rowsum,
-                      float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+                      float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
+                      float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
-  if (!v_w || !out || !rowmax || !rowsum || !P) return EP_ERR_NULL;
+  if (!v_w || !out || !S || !rowmax || !rowsum || !P) return EP_ERR_NULL;
   const Ws w = carve(B, N, D, M);
   if (w.total > 0 && (!workspace || workspace_bytes < w.total)) return EP_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
-    rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, rowmax, rowsum, attn, (char*)workspace + w.sm100, s);
+    rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, (char*)workspace + w.sm100, s);
   } else {
     if (rc) return rc;
     t_last_family = 1;
-    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, rowmax, rowsum, attn, s);
+    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, s);
   }
   if (rc) return rc;
   // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
@@ -142,11 +146,11 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
 }
 
 extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M,
-                           int d_out, const float* rowmax, const float* rowsum, float* d_cls_token, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           int d_out, const float* S, const float* rowmax, const float* rowsum, float* d_cls_token,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
-  if (!rowmax || !rowsum || !d_cls_token) return EP_ERR_NULL;
+  if (!S || !rowmax || !rowsum || !d_cls_token) return EP_ERR_NULL;
   const Ws w = carve(B, N, D, M);
   if (!workspace || workspace_bytes < w.total) return EP_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -155,7 +159,7 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
   float* slots = (float*)((char*)workspace + w.slots);
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
-    return sm100_pool_bwd(x, cls_token, scale, B, N, D, M, rowmax, rowsum, dP, delta, d_cls_token,
+    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, dP, delta, d_cls_token,
                           (char*)workspace + w.sm100, s);
   }
   if (rc) return rc;
@@ -165,14 +169,14 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
 }
 
 extern "C" int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale, int B, int N,
-                      int D, int M, int d_out, const float* rowmax, const float* rowsum, const float* P,
-                      const float* g_out, float* d_cls_token, float* d_v_w, float* d_v_b, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      int D, int M, int d_out, const float* S, const float* rowmax, const float* rowsum,
+                      const float* P, const float* g_out, float* d_cls_token, float* d_v_w, float* d_v_b,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
-  if (!v_w || !rowmax || !rowsum || !P || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
+  if (!v_w || !S || !rowmax || !rowsum || !P || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
   if ((rc = ep_bwd_proj(g_out, P, v_w, B, N, D, M, d_out, d_v_w, d_v_b, workspace, workspace_bytes, stream))) return rc;
-  return ep_bwd_pool(x, x_dtype, cls_token, scale, B, N, D, M, d_out, rowmax, rowsum, d_cls_token, workspace,
+  return ep_bwd_pool(x, x_dtype, cls_token, scale, B, N, D, M, d_out, S, rowmax, rowsum, d_cls_token, workspace,
                      workspace_bytes, stream);
 }
 
@@ -187,7 +191,8 @@ extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_to
   float* rowmax = (float*)workspace;
   float* rowsum = rowmax + (size_t)B * M;
   t_last_family = 1;
-  return pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, nullptr, rowmax, rowsum, attn, (cudaStream_t)stream);
+  return pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, nullptr, nullptr, rowmax, rowsum, attn,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,

@@ -69,7 +69,7 @@ int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s
 int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s);  // out[i] = a[i].b[i]
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
-                float* P, float* rowmax, float* rowsum, float* attn, cudaStream_t s);
+                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, cudaStream_t s);
 int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 const float* rowmax, const float* rowsum, const float* dP, const float* delta,
                 float* dq_slots, int n_slots, float* d_cls, cudaStream_t s);

@@ -1,12 +1,593 @@
-// tcgen05 / TMA pooling kernels -- placeholder until the fused kernels land: reports "unsupported"
-// so that dispatch uses the general kernels.
+// tcgen05 / TMA kernels for the EP pooling (sm_100a).
+//
+// The pooling is two contractions over the token tensor x (B, N, D) bf16:
+//   logit-type   Z[b,n,j] = sum_d x[b,n,d] * W[b?][j,d]        (S = q.x^T in forward, dA = dP.x^T in backward)
+//   pool-type    Y[b?][d,j] = sum_n x[b,n,d] * V[b,j,n]        (P = A x in forward,  dq = dS^T x in backward)
+// Both stream x from HBM exactly once through a TMA -> shared-memory ring and feed it to the tensor
+// core as the 128-row operand of tcgen05.mma (cta_group::1, M=128, bf16 in, fp32 accumulate in TMEM):
+//   ks_kernel : x chunk [128 tokens x 64 d] is the K-major A operand, W chunk [J x 64 d] the K-major B
+//               operand; the accumulators of ALL token tiles of a sample live in TMEM while the kernel
+//               walks d, so W is streamed once per sample and nothing large is resident.
+//   kp_kernel : the SAME 128-byte-swizzled x bytes are read as an MN-major A operand [128 d x 16 tokens]
+//               (instruction-descriptor transpose bit), V is written by a converter warpgroup as a
+//               K-major B operand [J x 64 tokens]; the (d x J) accumulators stay in TMEM per sample
+//               (forward) or for the whole launch (backward, gradients summed over the batch).
+// fp32 operands (queries, probabilities, gradients) enter as bf16 hi/lo pairs in adjacent operand
+// rows (j = 2m: hi, 2m+1: lo), so every product is exact and the sum carries ~16 mantissa bits; the
+// two accumulator columns are added when the result leaves TMEM.
+// Warp roles (one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (ks) / operand converter (kp), warps 8-11 = epilogue (kp).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "ep_ptx.cuh"
 #include "ep_sm100.cuh"
 
 namespace ep {
-bool sm100_supported(int, int, int, int, int) { return false; }
-size_t sm100_workspace_bytes(int, int, int, int) { return 0; }
-int sm100_pool_fwd(const void*, const float*, float, int, int, int, int, float*, float*, float*, float*, void*,
-                   cudaStream_t) { return EP_ERR_UNSUPPORTED; }
-int sm100_pool_bwd(const void*, const float*, float, int, int, int, int, const float*, const float*, const float*,
-                   const float*, float*, void*, cudaStream_t) { return EP_ERR_UNSUPPORTED; }
+using namespace ptx;
+
+constexpr int kTileRows = 128;    // ks: token rows per MMA tile (UMMA M)
+constexpr int kChunkD = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kXChunkBytes = kTileRows * 128;   // 16 KB
+constexpr int kTokBlock = 64;     // kp: tokens per operand block (4 MMA K-steps)
+constexpr int kBrickBytes = 2 * kTokBlock * 128;   // [64 tokens x 128 d] = two swizzled halves, 16 KB
+constexpr int kSmemBudget = 220 * 1024;
+
+struct KSParams {
+  int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols;
+  float* out;            // (B, M, N)
+  const float* S;        // mode 1: saved logits
+  const float* rmax;     // mode 1
+  const float* rsum;     // mode 1
+  const float* delta;    // mode 1
+};
+
+struct KPParams {
+  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols;
+  const float* src;      // (B, M, N): logits (mode 0) or dS (mode 1)
+  const float* rmax;     // mode 0
+  const float* rsum;     // mode 0
+  float* out;            // mode 0: P (B, M, D); mode 1: partial dq (gridDim.x, M, D)
+};
+
+// ------------------------------------------------------------------------------------------------
+// logit-type kernel
+// ------------------------------------------------------------------------------------------------
+template <int kMode>
+__global__ void __launch_bounds__(256, 1)
+ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const KSParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_bytes = (uint32_t)p.J * 128u;
+  const uint32_t stage_bytes = w_bytes + (uint32_t)p.G * kXChunkBytes;
+  const uint32_t bar_base = smem_base + (uint32_t)p.nstages * stage_bytes;
+  // barriers: full[nstages], empty[nstages], tmem_full[2], tmem_empty[2], then the TMEM base address word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.nstages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * p.nstages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * p.nstages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.nstages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); }
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int nitems = p.B * p.ngroups;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_x = policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int b = item / p.ngroups, g = item - b * p.ngroups;
+        const int t0 = g * p.G, gt = min(p.G, p.ntiles - t0);
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), w_bytes + (uint32_t)gt * kXChunkBytes);
+          tma_load_3d(dst, &tm_w, full_bar(s), c * kChunkD, 0, p.w_batched ? b : 0);
+          for (int t = 0; t < gt; ++t)
+            tma_load_3d_hint(dst + w_bytes + (uint32_t)t * kXChunkBytes, &tm_x, full_bar(s), c * kChunkD,
+                             (t0 + t) * kTileRows, b, pol_x);
+          if (++s == p.nstages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, p.J, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const int g = item % p.ngroups;
+        const int gt = min(p.G, p.ntiles - g * p.G);
+        const int buf = it % p.nbuf;
+        mbar_wait(tempty_bar(buf), (((uint32_t)(it / p.nbuf)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.bufcols);
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t wsm = smem_base + (uint32_t)s * stage_bytes;
+          for (int t = 0; t < gt; ++t) {
+            const uint32_t xsm = wsm + w_bytes + (uint32_t)t * kXChunkBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(acc + (uint32_t)(t * p.J), smem_desc_sw128(xsm + 32u * k, 16, 1024),
+                       smem_desc_sw128(wsm + 32u * k, 16, 1024), idesc, (uint32_t)((c | k) != 0));
+          }
+          umma_commit(empty_bar(s));
+          if (++s == p.nstages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp - 4;
+    int it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int b = item / p.ngroups, g = item - b * p.ngroups;
+      const int t0 = g * p.G, gt = min(p.G, p.ntiles - t0);
+      const int buf = it % p.nbuf;
+      mbar_wait(tfull_bar(buf), ((uint32_t)(it / p.nbuf)) & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
+      for (int t = 0; t < gt; ++t) {
+        const int n = (t0 + t) * kTileRows + wq * 32 + lane;
+        for (int j0 = 0; j0 < p.J; j0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + (uint32_t)(t * p.J + j0), r);
+          tmem_ld_wait();
+          if (n < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = (j0 >> 1) + i;
+              if (m < p.M) {
+                float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
+                const size_t bm = (size_t)b * p.M + m;
+                if (kMode == 1) {
+                  const float a = __expf(p.S[bm * p.N + n] - p.rmax[bm]) / p.rsum[bm];
+                  v = a * (v - p.delta[bm]);
+                }
+                p.out[bm * p.N + n] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool-type kernel
+// ------------------------------------------------------------------------------------------------
+template <int kMode>
+__global__ void __launch_bounds__(384, 1)
+kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t wt_bytes = (uint32_t)p.J * 128u;
+  const uint32_t wt_base = smem_base + (uint32_t)p.xslots * kBrickBytes;
+  const uint32_t bar_base = wt_base + (uint32_t)p.wslots * wt_bytes;
+  auto xfull = [&](int s) { return bar_base + 8u * s; };
+  auto xempty = [&](int s) { return bar_base + 8u * (p.xslots + s); };
+  auto wfull = [&](int s) { return bar_base + 8u * (2 * p.xslots + s); };
+  auto wempty = [&](int s) { return bar_base + 8u * (2 * p.xslots + p.wslots + s); };
+  auto afull = [&](int b) { return bar_base + 8u * (2 * p.xslots + 2 * p.wslots + b); };
+  auto aempty = [&](int b) { return bar_base + 8u * (2 * p.xslots + 2 * p.wslots + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.xslots + 2 * p.wslots + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.xslots; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
+    for (int s = 0; s < p.wslots; ++s) { mbar_init(wfull(s), 128); mbar_init(wempty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(afull(b), 1); mbar_init(aempty(b), 128); }
+    fence_barrier_init();
+  }
+  // operand rows that no query owns (2M..J-1) stay zero for the whole launch
+  for (uint32_t i = threadIdx.x; i < (uint32_t)p.wslots * wt_bytes / 16u; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_gen + (wt_base - smem_base))[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) prefetch_tmap(&tm_x);
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int d0 = blockIdx.y * p.nsl * 128;
+  const int nsl = min(p.nsl, p.D / 128 - blockIdx.y * p.nsl);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_x = policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x)
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int sl = 0; sl < nsl; ++sl) {
+            mbar_wait(xempty(s), ph ^ 1u);
+            const uint32_t dst = smem_base + (uint32_t)s * kBrickBytes;
+            mbar_arrive_expect_tx(xfull(s), kBrickBytes);
+            tma_load_3d_hint(dst, &tm_x, xfull(s), d0 + sl * 128, kb * kTokBlock, b, pol_x);
+            tma_load_3d_hint(dst + kBrickBytes / 2, &tm_x, xfull(s), d0 + sl * 128 + 64, kb * kTokBlock, b, pol_x);
+            if (++s == p.xslots) { s = 0; ph ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, p.J, 1, 0);       // A (tokens as K) is MN-major
+      int xs = 0, ws = 0, it = 0;
+      uint32_t xph = 0, wph = 0;
+      bool first = true;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+        const int buf = (kMode == 0) ? it % p.nbuf : 0;
+        if (kMode == 0) {
+          mbar_wait(aempty(buf), (((uint32_t)(it / p.nbuf)) & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.bufcols);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(wfull(ws), wph);
+          tc_fence_after();
+          const uint32_t wsm = wt_base + (uint32_t)ws * wt_bytes;
+          for (int sl = 0; sl < nsl; ++sl) {
+            mbar_wait(xfull(xs), xph);
+            tc_fence_after();
+            const uint32_t xsm = smem_base + (uint32_t)xs * kBrickBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accum = (kMode == 0) ? (uint32_t)((kb | k) != 0) : (uint32_t)(!(first && kb == 0 && k == 0));
+              umma_f16(acc + (uint32_t)(sl * p.J), smem_desc_sw128(xsm + 2048u * k, kBrickBytes / 2, 1024),
+                       smem_desc_sw128(wsm + 32u * k, 16, 1024), idesc, accum);
+            }
+            umma_commit(xempty(xs));
+            if (++xs == p.xslots) { xs = 0; xph ^= 1u; }
+          }
+          umma_commit(wempty(ws));
+          if (++ws == p.wslots) { ws = 0; wph ^= 1u; }
+        }
+        first = false;
+        if (kMode == 0) umma_commit(afull(buf));
+      }
+      if (kMode == 1) umma_commit(afull(0));
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // converter: fp32 (B, M, N) -> bf16 hi/lo K-major operand block [J rows x 64 tokens], 128B-swizzled
+    const int tid = threadIdx.x - 128;
+    const int t = tid & 63, half = tid >> 6;
+    int ws = 0;
+    uint32_t wph = 0;
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x)
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(wempty(ws), wph ^ 1u);
+        uint8_t* wt = smem_gen + (wt_base - smem_base) + (size_t)ws * wt_bytes;
+        const int n = kb * kTokBlock + t;
+        for (int m = half; m < p.M; m += 2) {
+          const size_t bm = (size_t)b * p.M + m;
+          float e = 0.f;
+          if (n < p.N) {
+            e = p.src[bm * p.N + n];
+            if (kMode == 0) e = __expf(e - p.rmax[bm]);
+          }
+          const __nv_bfloat16 hi = __float2bfloat16_rn(e);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
+          const uint32_t col = (uint32_t)(t & 7) * 2u;
+          *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m, t >> 3) + col) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m + 1, t >> 3) + col) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(wfull(ws));
+        if (++ws == p.wslots) { ws = 0; wph ^= 1u; }
+      }
+  } else if (warp >= 8) {
+    const int wq = warp - 8;
+    auto drain = [&](int buf, int b) {
+      const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
+      for (int sl = 0; sl < nsl; ++sl) {
+        const int d = d0 + sl * 128 + wq * 32 + lane;
+        for (int j0 = 0; j0 < p.J; j0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + (uint32_t)(sl * p.J + j0), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = (j0 >> 1) + i;
+            if (m < p.M) {
+              float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
+              if (kMode == 0) {
+                v /= p.rsum[(size_t)b * p.M + m];
+                p.out[((size_t)b * p.M + m) * p.D + d] = v;
+              } else {
+                p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
+              }
+            }
+          }
+        }
+      }
+    };
+    if (kMode == 0) {
+      int it = 0;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+        const int buf = it % p.nbuf;
+        mbar_wait(afull(buf), ((uint32_t)(it / p.nbuf)) & 1u);
+        tc_fence_after();
+        drain(buf, b);
+        tc_fence_before();
+        mbar_arrive(aempty(buf));
+      }
+    } else {
+      mbar_wait(afull(0), 0);
+      tc_fence_after();
+      drain(0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers: hi/lo split of fp32 operands, row statistics of the logits, partial reduction
+// ------------------------------------------------------------------------------------------------
+// dst[(z*J + 2m + {0,1}) * D + d] = hi/lo(scale * src[(z*M + m) * D + d]); rows 2M..J-1 zero.
+__global__ void split_hilo_kernel(const float* __restrict__ src, float scale, int M, int J, int D,
+                                  __nv_bfloat16* __restrict__ dst) {
+  const int z = blockIdx.y;
+  const int pairs = J / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)pairs * D / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (D / 4)), d = (int)(i % (D / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M) v = *reinterpret_cast<const float4*>(src + ((size_t)z * M + m) * D + d);
+    const float f[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = __float2bfloat16_rn(f[e]);
+      lo[e] = __float2bfloat16_rn(f[e] - __bfloat162float(hi[e]));
+    }
+    __nv_bfloat16* ph = dst + ((size_t)z * J + 2 * m) * D + d;
+    *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(ph + D) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+
+// one warp per (b, m) row of the logits: rowmax, rowsum = sum exp(S - rowmax), optional attention map
+__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ S, long long rows, int N,
+                                                       float* __restrict__ rmax, float* __restrict__ rsum,
+                                                       float* __restrict__ attn) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* row = S + r * N;
+  float mx = -INFINITY;
+  for (int n = lane; n < N; n += 32) mx = fmaxf(mx, row[n]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int n = lane; n < N; n += 32) sum += __expf(row[n] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) { rmax[r] = mx; rsum[r] = sum; }
+  if (attn) {
+    const float inv = 1.f / sum;
+    for (int n = lane; n < N; n += 32) attn[r * N + n] = __expf(row[n] - mx) * inv;
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t n, float scale,
+                                       float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < nparts; ++k) s += part[(size_t)k * n + i];
+  out[i] = s * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 tensor (d2, d1, d0) row-major, box (1, rows, 64 elements), 128-byte swizzle, zero fill out of bounds
+int make_tmap(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return EP_ERR_DEVICE;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : EP_ERR_UNSUPPORTED;
+}
+
+int round16(int v) { return (v + 15) / 16 * 16; }
+int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
+
+struct Plan {
+  bool ok = false;
+  int J, ntiles, G, ngroups, ks_stages, ks_nbuf, nkb, nsl_fwd, nsl_bwd, ysplit_fwd, ysplit_bwd, xslots, wslots;
+  size_t ks_smem, kp_smem;
+};
+
+Plan make_plan(int N, int D, int M) {
+  Plan pl;
+  if (D % 128 != 0 || M < 1 || M > 64) return pl;
+  pl.J = round16(2 * M);
+  pl.ntiles = (N + kTileRows - 1) / kTileRows;
+  // tiles of one sample handled together: bounded by TMEM columns (512) and by two smem stages
+  int G = std::min(pl.ntiles, 512 / pl.J);
+  while (G > 1 && 2 * ((size_t)pl.J * 128 + (size_t)G * kXChunkBytes) > (size_t)kSmemBudget) --G;
+  if (G < 1 || 2 * ((size_t)pl.J * 128 + (size_t)G * kXChunkBytes) > (size_t)kSmemBudget) return pl;
+  pl.ngroups = (pl.ntiles + G - 1) / G;
+  G = (pl.ntiles + pl.ngroups - 1) / pl.ngroups;            // balance the groups
+  pl.G = G;
+  const size_t stage = (size_t)pl.J * 128 + (size_t)G * kXChunkBytes;
+  pl.ks_stages = (int)std::min<size_t>(6, kSmemBudget / stage);
+  pl.ks_nbuf = (2 * G * pl.J <= 512) ? 2 : 1;
+  pl.ks_smem = pl.ks_stages * stage + 1024 + 256;
+  pl.nkb = (N + kTokBlock - 1) / kTokBlock;
+  const int slices = D / 128;
+  const int max_sl_fwd = std::max(1, 256 / pl.J), max_sl_bwd = std::max(1, 512 / pl.J);   // fwd double-buffers TMEM
+  pl.ysplit_fwd = (slices + max_sl_fwd - 1) / max_sl_fwd;
+  pl.nsl_fwd = (slices + pl.ysplit_fwd - 1) / pl.ysplit_fwd;
+  pl.ysplit_bwd = (slices + max_sl_bwd - 1) / max_sl_bwd;
+  pl.nsl_bwd = (slices + pl.ysplit_bwd - 1) / pl.ysplit_bwd;
+  pl.wslots = 4;
+  pl.xslots = (int)std::min<size_t>(10, (kSmemBudget - (size_t)pl.wslots * pl.J * 128) / kBrickBytes);
+  pl.kp_smem = (size_t)pl.xslots * kBrickBytes + (size_t)pl.wslots * pl.J * 128 + 1024 + 512;
+  pl.ok = pl.xslots >= 3 && pl.ks_stages >= 2;
+  return pl;
+}
+
+struct Ws100 {
+  size_t qhl, S_unused, dphl, dS, part, total;
+};
+Ws100 carve100(int B, int N, int D, int M, const Plan& pl) {
+  Ws100 w;
+  size_t off = 0;
+  w.qhl = off;  off += align_up((size_t)pl.J * D * 2, 256);
+  w.dphl = off; off += align_up((size_t)B * pl.J * D * 2, 256);
+  w.dS = off;   off += align_up((size_t)B * M * N * 4, 256);
+  w.part = off; off += align_up((size_t)kNumSMs * M * D * 4, 256);
+  w.S_unused = 0;
+  w.total = off;
+  return w;
+}
+
+template <typename K>
+int set_dyn_smem(K kernel, size_t bytes) {
+  EP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int kMode>
+int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, int M, const Plan& pl, float* out,
+              const float* S, const float* rmax, const float* rsum, const float* delta, cudaStream_t s) {
+  CUtensorMap tm_x, tm_w;
+  int rc;
+  if ((rc = make_tmap(&tm_x, x, D, N, B, kTileRows))) return rc;
+  if ((rc = make_tmap(&tm_w, w, D, pl.J, w_batched ? B : 1, pl.J))) return rc;
+  KSParams p{};
+  p.B = B; p.N = N; p.D = D; p.M = M; p.J = pl.J; p.ntiles = pl.ntiles; p.G = pl.G; p.ngroups = pl.ngroups;
+  p.nchunks = D / kChunkD; p.nstages = pl.ks_stages; p.w_batched = w_batched; p.nbuf = pl.ks_nbuf;
+  p.bufcols = pl.G * pl.J; p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
+  p.out = out; p.S = S; p.rmax = rmax; p.rsum = rsum; p.delta = delta;
+  if ((rc = set_dyn_smem(ks_kernel<kMode>, pl.ks_smem))) return rc;
+  const int grid = std::min(B * pl.ngroups, kNumSMs);
+  ks_kernel<kMode><<<grid, 256, pl.ks_smem, s>>>(tm_x, tm_w, p);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int kMode>
+int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const float* src, const float* rmax,
+              const float* rsum, float* out, int* groups_out, cudaStream_t s) {
+  CUtensorMap tm_x;
+  int rc;
+  if ((rc = make_tmap(&tm_x, x, D, N, B, kTokBlock))) return rc;
+  KPParams p{};
+  p.B = B; p.N = N; p.D = D; p.M = M; p.J = pl.J; p.nkb = pl.nkb;
+  p.nsl = kMode == 0 ? pl.nsl_fwd : pl.nsl_bwd;
+  const int ysplit = kMode == 0 ? pl.ysplit_fwd : pl.ysplit_bwd;
+  p.xslots = pl.xslots; p.wslots = pl.wslots;
+  p.bufcols = p.nsl * pl.J;
+  p.nbuf = (kMode == 0 && 2 * p.bufcols <= 512) ? 2 : 1;
+  p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
+  p.src = src; p.rmax = rmax; p.rsum = rsum; p.out = out;
+  if ((rc = set_dyn_smem(kp_kernel<kMode>, pl.kp_smem))) return rc;
+  const int gx = std::max(1, std::min(B, kNumSMs / ysplit));
+  if (groups_out) *groups_out = gx;
+  kp_kernel<kMode><<<dim3(gx, ysplit), 384, pl.kp_smem, s>>>(tm_x, p);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+bool sm100_supported(int x_dtype, int B, int N, int D, int M) {
+  if (x_dtype != EP_DTYPE_BF16 || B < 1 || N < 1) return false;
+  return make_plan(N, D, M).ok && encode_fn() != nullptr;
+}
+
+size_t sm100_workspace_bytes(int B, int N, int D, int M) {
+  Plan pl = make_plan(N, D, M);
+  if (!pl.ok) return 0;
+  return carve100(B, N, D, M, pl).total;
+}
+
+int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, int D, int M, float* P, float* S,
+                   float* rowmax, float* rowsum, float* attn, void* ws, cudaStream_t s) {
+  const Plan pl = make_plan(N, D, M);
+  if (!pl.ok) return EP_ERR_UNSUPPORTED;
+  const Ws100 w = carve100(B, N, D, M, pl);
+  __nv_bfloat16* qhl = (__nv_bfloat16*)((char*)ws + w.qhl);
+  int rc;
+  split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
+  EP_LAUNCH_CHECK();
+  if ((rc = launch_ks<0>(x, qhl, 0, B, N, D, M, pl, S, nullptr, nullptr, nullptr, nullptr, s))) return rc;
+  const long long rows = (long long)B * M;
+  rowstats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, rows, N, rowmax, rowsum, attn);
+  EP_LAUNCH_CHECK();
+  if (P == nullptr) return 0;
+  return launch_kp<0>(x, B, N, D, M, pl, S, rowmax, rowsum, P, nullptr, s);
+}
+
+int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int D, int M, const float* rowmax,
+                   const float* rowsum, const float* dP, const float* delta, float* d_cls, void* ws, cudaStream_t s) {
+  const Plan pl = make_plan(N, D, M);
+  if (!pl.ok) return EP_ERR_UNSUPPORTED;
+  const Ws100 w = carve100(B, N, D, M, pl);
+  __nv_bfloat16* dphl = (__nv_bfloat16*)((char*)ws + w.dphl);
+  float* dS = (float*)((char*)ws + w.dS);
+  float* part = (float*)((char*)ws + w.part);
+  int rc;
+  split_hilo_kernel<<<dim3(std::max(1, std::min(64, pl.J * D / 8 / 256)), B), 256, 0, s>>>(dP, 1.f, M, pl.J, D, dphl);
+  EP_LAUNCH_CHECK();
+  if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, dS, S, rowmax, rowsum, delta, s))) return rc;
+  int groups = 0;
+  if ((rc = launch_kp<1>(x, B, N, D, M, pl, dS, nullptr, nullptr, part, &groups, s))) return rc;
+  const size_t n = (size_t)M * D;
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, groups, n, scale, d_cls);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ep

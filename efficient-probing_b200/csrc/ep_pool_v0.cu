@@ -94,8 +94,8 @@ __device__ __forceinline__ void pool_phase(const XT* __restrict__ xb, const floa
 template <typename XT>
 __global__ void __launch_bounds__(kThreads)
 pool_fwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, float scale, int N, int D, int M,
-                   float* __restrict__ P, float* __restrict__ rowmax, float* __restrict__ rowsum,
-                   float* __restrict__ attn) {
+                   float* __restrict__ P, float* __restrict__ S_out, float* __restrict__ rowmax,
+                   float* __restrict__ rowsum, float* __restrict__ attn) {
   extern __shared__ __align__(16) float S[];
   const int b = blockIdx.x, LD = s_ld(M);
   const XT* xb = x + (size_t)b * N * D;
@@ -107,7 +107,11 @@ pool_fwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, floa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int m = warp; m < M; m += kThreads / 32) {
     float mx = -INFINITY;
-    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, S[n * LD + m]);
+    for (int n = lane; n < N; n += 32) {
+      const float v = S[n * LD + m];
+      mx = fmaxf(mx, v);
+      if (S_out) S_out[((size_t)b * M + m) * N + n] = v;         // logits, saved for the backward pass
+    }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int n = lane; n < N; n += 32) { const float e = expf(S[n * LD + m] - mx); S[n * LD + m] = e; sum += e; }
@@ -180,17 +184,17 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
-                float* P, float* rowmax, float* rowsum, float* attn, cudaStream_t s) {
+                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, cudaStream_t s) {
   if (M > 64) return EP_ERR_UNSUPPORTED;
   const size_t smem = pool_v0_smem_bytes(N, M);
   int rc;
   if (x_dtype == EP_DTYPE_BF16) {
     if ((rc = set_smem(pool_fwd_v0_kernel<__nv_bfloat16>, smem))) return rc;
     pool_fwd_v0_kernel<__nv_bfloat16><<<B, kThreads, smem, s>>>((const __nv_bfloat16*)x, cls, scale, N, D, M, P,
-                                                                 rowmax, rowsum, attn);
+                                                                 S_out, rowmax, rowsum, attn);
   } else {
     if ((rc = set_smem(pool_fwd_v0_kernel<float>, smem))) return rc;
-    pool_fwd_v0_kernel<float><<<B, kThreads, smem, s>>>((const float*)x, cls, scale, N, D, M, P, rowmax, rowsum, attn);
+    pool_fwd_v0_kernel<float><<<B, kThreads, smem, s>>>((const float*)x, cls, scale, N, D, M, P, S_out, rowmax, rowsum, attn);
   }
   EP_LAUNCH_CHECK();
   return 0;

@@ -41,16 +41,17 @@ class EPPoolFunction(torch.autograd.Function):
         rowmax = torch.empty(B, M, dtype=torch.float32, device=dev)
         rowsum = torch.empty(B, M, dtype=torch.float32, device=dev)
         P = torch.empty(B, M, D, dtype=torch.float32, device=dev)
+        S = torch.empty(B, M, N, dtype=torch.float32, device=dev)
         attn = torch.empty(B, M, N, dtype=torch.float32, device=dev) if return_attn else None
         nbytes = lib.ep_workspace_bytes(B, N, D, M, d_out)
         ws = _workspace(x, nbytes)
         with torch.cuda.device(dev):
             rc = lib.ep_fwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), _lib.ptr(b32),
-                            float(scale), B, N, D, M, int(d_out), out.data_ptr(), rowmax.data_ptr(),
+                            float(scale), B, N, D, M, int(d_out), out.data_ptr(), S.data_ptr(), rowmax.data_ptr(),
                             rowsum.data_ptr(), P.data_ptr(), _lib.ptr(attn), ws.data_ptr(), ws.numel(),
                             _lib.stream_ptr(dev))
         _lib.check(rc, "ep_fwd")
-        ctx.save_for_backward(x, cls32, w32, rowmax, rowsum, P)
+        ctx.save_for_backward(x, cls32, w32, S, rowmax, rowsum, P)
         ctx.meta = (float(scale), M, int(d_out), v_bias is not None, cls_token.dtype, v_weight.dtype)
         ctx.x_needs_grad = x.requires_grad
         if return_attn:
@@ -64,7 +65,7 @@ class EPPoolFunction(torch.autograd.Function):
             raise NotImplementedError("dL/dx is not produced: the EP probe trains on a frozen backbone "
                                       "(main_linprobe.py:393-400); --finetuning is out of scope")
         lib = _lib.load()
-        x, cls32, w32, rowmax, rowsum, P = ctx.saved_tensors
+        x, cls32, w32, S, rowmax, rowsum, P = ctx.saved_tensors
         scale, M, d_out, has_bias, cls_dtype, w_dtype = ctx.meta
         B, N, D = x.shape
         dev = x.device
@@ -75,7 +76,8 @@ class EPPoolFunction(torch.autograd.Function):
         ws = _workspace(x, lib.ep_workspace_bytes(B, N, D, M, d_out))
         with torch.cuda.device(dev):
             rc = lib.ep_bwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), scale,
-                            B, N, D, M, d_out, rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(), g.data_ptr(),
+                            B, N, D, M, d_out, S.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(),
+                            g.data_ptr(),
                             d_cls.data_ptr(), d_w.data_ptr(), _lib.ptr(d_b), ws.data_ptr(), ws.numel(),
                             _lib.stream_ptr(dev))
         _lib.check(rc, "ep_bwd")

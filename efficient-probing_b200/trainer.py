@@ -84,6 +84,7 @@ class EPHeadTrainer:
         self.rowmax = torch.empty(B, M, **f32)
         self.rowsum = torch.empty(B, M, **f32)
         self.P = torch.empty(B, M, D, **f32)
+        self.S = torch.empty(B, M, N, **f32)               # logits, saved for the backward pass
         self.y = torch.empty(B, Dp, **f32)
         self.save_mean = torch.empty(Dp, **f32)
         self.save_invstd = torch.empty(Dp, **f32)
@@ -114,8 +115,8 @@ class EPHeadTrainer:
         pool, bn, fc = self.pool, self.bn, self.fc
         _lib.check(lib.ep_fwd(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
                               pool.v.weight.data_ptr(), _lib.ptr(pool.v.bias), float(pool.scale), B, N, D, M, self.d_out,
-                              self.out.data_ptr(), self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.P.data_ptr(),
-                              None, self.ws.data_ptr(), self.ws.numel(), s), "ep_fwd")
+                              self.out.data_ptr(), self.S.data_ptr(), self.rowmax.data_ptr(), self.rowsum.data_ptr(),
+                              self.P.data_ptr(), None, self.ws.data_ptr(), self.ws.numel(), s), "ep_fwd")
         _lib.check(lib.ep_bn_fwd(self.out.data_ptr(), B, Dp, float(bn.eps), float(bn.momentum), int(training),
                                  bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                  bn.num_batches_tracked.data_ptr(), self.y.data_ptr(), self.save_mean.data_ptr(),
@@ -148,8 +149,8 @@ class EPHeadTrainer:
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(self.flat_grad[:self.n_early], group=self.group)
         _lib.check(lib.ep_bwd_pool(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
-                                   float(pool.scale), B, N, D, M, self.d_out, self.rowmax.data_ptr(),
-                                   self.rowsum.data_ptr(), self.g["cls"].data_ptr(), self.ws.data_ptr(),
+                                   float(pool.scale), B, N, D, M, self.d_out, self.S.data_ptr(),
+                                   self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.g["cls"].data_ptr(), self.ws.data_ptr(),
                                    self.ws.numel(), s), "ep_bwd_pool")
         if self.world > 1:
             if self.overlap_comm:

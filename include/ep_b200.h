@@ -50,6 +50,9 @@ int ep_device_check(void);
 int ep_set_kernel_mode(int mode);
 /* Which family the last ep_fwd/ep_bwd call on this thread used (1 = general, 2 = tcgen05). */
 int ep_last_kernel_family(void);
+/* Which family ep_fwd/ep_bwd would use for this shape under the current mode (0 = none: forced tcgen05
+ * but unsupported). */
+int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M);
 /* Number of kernels this library has launched in this process (host-side count; launches replayed by a
  * CUDA graph are not seen here -- count the captured step once and multiply). */
 unsigned long long ep_launch_count(void);
@@ -60,12 +63,12 @@ size_t ep_workspace_bytes(int B, int N, int D, int M, int d_out);
 /* EfficientProbing.forward -- poolings/ep.py:28-47 (num_heads == 1).
  *   S[b,m,n] = scale * cls_token[m] . x[b,n];  A = softmax_n(S);  P[b,m] = sum_n A[b,m,n] x[b,n];
  *   out[b, m*c:(m+1)*c] = v_w[m*c:(m+1)*c] @ P[b,m] (+ v_b),  c = D / (d_out*M).
- * Outputs: out (B, D/d_out); saved for backward: rowmax, rowsum (B, M) -- the shift and the
- * normaliser of the softmax (A = exp(S - rowmax) / rowsum) -- and P (B, M, D).
+ * Outputs: out (B, D/d_out); saved for backward: the logits S (B, M, N), rowmax, rowsum (B, M) -- the
+ * shift and the normaliser of the softmax (A = exp(S - rowmax) / rowsum) -- and P (B, M, D).
  * attn (B, M, N) is written when non-NULL (the attention maps of tools/ep_attention_maps.py:51-58). */
 int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
            float scale, int B, int N, int D, int M, int d_out,
-           float* out, float* rowmax, float* rowsum, float* P, float* attn,
+           float* out, float* S, float* rowmax, float* rowsum, float* P, float* attn,
            void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of ep_fwd (replaces autograd through ep.py:35-45; engine_finetune.py:73 -> misc.py:267).
@@ -73,7 +76,7 @@ int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w,
  * nullable).  The frozen-backbone path needs no dL/dx (main_linprobe.py:393-400). */
 int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale,
            int B, int N, int D, int M, int d_out,
-           const float* rowmax, const float* rowsum, const float* P, const float* g_out,
+           const float* S, const float* rowmax, const float* rowsum, const float* P, const float* g_out,
            float* d_cls_token, float* d_v_w, float* d_v_b,
            void* workspace, size_t workspace_bytes, void* stream);
 
@@ -86,7 +89,7 @@ int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w,
 int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int B, int N, int D, int M, int d_out,
                 float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes, void* stream);
 int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M, int d_out,
-                const float* rowmax, const float* rowsum, float* d_cls_token,
+                const float* S, const float* rowmax, const float* rowsum, float* d_cls_token,
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* tools/ep_attention_maps.py:51-58 for a batch: attn[b] = softmax(scale * cls_token @ x[b]^T), (B, M, N). */

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_rejection_needs_no_gpu():
     L = E._lib.load()
     # NULL pointers / bad shapes are rejected before any CUDA call
-    assert L.ep_fwd(None, 0, None, None, None, 1.0, 1, 1, 8, 1, 1, None, None, None, None, None, None, 0, None) == -1
+    assert L.ep_fwd(None, 0, None, None, None, 1.0, 1, 1, 8, 1, 1, None, None, None, None, None, None, None, 0, None) == -1
     assert L.ep_workspace_bytes(0, 1, 1, 1, 1) == 0
     assert L.ep_workspace_bytes(4, 19, 64, 8, 1) > 0
     assert L.ep_set_kernel_mode(7) == -2 and L.ep_set_kernel_mode(0) == 0
