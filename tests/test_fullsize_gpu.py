@@ -15,14 +15,26 @@ def _tokens(B, N, D, seed):
     return torch.randn(B, N, D, device=DEV, generator=g).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("B,N,D,M", [(1024, 257, 1024, 32), (1024, 257, 1024, 8), (256, 730, 1664, 32)])
-def test_fullsize_properties(B, N, D, M):
+@pytest.fixture(params=[1, 2], ids=["general", "tcgen05"])
+def family(request):
+    lib = E._lib.load()
+    lib.ep_set_kernel_mode(request.param)
+    yield request.param
+    lib.ep_set_kernel_mode(0)
+
+
+@pytest.mark.parametrize("B,N,D,M", [(1024, 257, 1024, 32), (1024, 257, 1024, 8), (256, 730, 1664, 32),
+                                     (256, 201, 4096, 32), (1024, 256, 1152, 32)])
+def test_fullsize_properties(B, N, D, M, family):
+    if family == 1 and D > 1664:
+        pytest.skip("general kernels at D=4096: covered at small batch in test_parity_gpu")
     torch.manual_seed(0)
     pool = E.EfficientProbing(D, num_queries=M).to(DEV)
     with torch.no_grad():
         pool.cls_token.mul_(20.0)                      # non-trivial attention
     x = _tokens(B, N, D, 1234)
     out = pool(x)
+    assert E._lib.load().ep_last_kernel_family() == family
     attn = pool.attention_maps(x)
     # (1) attention rows are distributions
     assert float((attn.sum(-1) - 1).abs().max()) < 1e-4 and float(attn.min()) >= 0
@@ -62,7 +74,7 @@ def test_fullsize_properties(B, N, D, M):
         assert abs(fd - an) <= 2e-2 * max(abs(fd), abs(an)) + 1e-3, (fd, an)
 
 
-def test_top1_identical_on_10k_samples():
+def test_top1_identical_on_10k_samples(family):
     """BASELINE.json: identical top-1 predictions on a fixed 10k-sample set (config-1 token shape)."""
     N, D, M, K, B = 197, 768, 8, 1000, 500
     torch.manual_seed(0)

@@ -15,6 +15,20 @@ TOL_FWD, TOL_GRAD = 1e-3, 2e-3
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=[1, 2], ids=["general", "tcgen05"])
+def family(request):
+    """Force one kernel family of the pooling (ep_set_kernel_mode) for the duration of a test."""
+    lib = E._lib.load()
+    lib.ep_set_kernel_mode(request.param)
+    yield request.param
+    lib.ep_set_kernel_mode(0)
+
+
+def require_family(family, B, N, D, M, dtype=torch.bfloat16):
+    if E._lib.load().ep_kernel_family_for(0 if dtype == torch.bfloat16 else 1, B, N, D, M) != family:
+        pytest.skip("shape not covered by the tcgen05 kernels (D % 128 != 0 or fp32 tokens)")
+
+
 def head_from_params(p: O.EPParams, K):
     D = p.cls_token.shape[2]
     h = E.make_ep_head(D, p.num_queries, K, d_out=p.d_out, qkv_bias=p.v_bias is not None)
@@ -88,6 +102,16 @@ def test_trainer_two_lars_steps_vs_reference_golden(name, graph):
     close(tr2.eval_logits(x), g.t("f64.eval_logits"), TOL_FWD, "eval logits")
 
 
+def test_auto_mode_prefers_tcgen05_for_baseline_shapes():
+    lib = E._lib.load()
+    lib.ep_set_kernel_mode(0)
+    for (N, D) in [(197, 768), (257, 1024), (256, 1152), (730, 1664), (201, 4096)]:
+        for M in (8, 32):
+            assert lib.ep_kernel_family_for(0, 1024, N, D, M) == 2, (N, D, M)
+    assert lib.ep_kernel_family_for(1, 8, 197, 768, 8) == 1       # fp32 tokens: general kernels
+    assert lib.ep_kernel_family_for(0, 8, 50, 72, 8) == 1         # D % 128 != 0: general kernels
+
+
 CASES = [  # B, N, D, M, K, d_out, bias, spread, q_gain
     (8, 197, 768, 8, 1000, 1, False, 1.0, 1.0),        # BASELINE config 1 shape (smaller batch)
     (4, 257, 1024, 32, 1000, 1, False, 1.0, 25.0),     # config 2 shape, sharpened attention
@@ -97,12 +121,15 @@ CASES = [  # B, N, D, M, K, d_out, bias, spread, q_gain
     (5, 50, 384, 12, 10, 2, True, 8.0, 20.0),          # d_out=2, bias, M not a power of two, logits ~ +-30
     (1, 1, 64, 8, 4, 1, False, 1.0, 1.0),              # single token: attention == 1
     (3, 1370, 768, 8, 10, 1, False, 1.0, 5.0),         # Franca@518 token count
+    (150, 129, 256, 16, 10, 1, False, 1.0, 10.0),      # more samples than SMs, one token past a tile edge
+    (7, 128, 128, 64, 10, 1, False, 1.0, 10.0),        # M = 64 (widest operand), N exactly one tile
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_N%d_D%d_M%d_K%d_do%d_b%d" % c[:7])
-def test_seeded_shapes_vs_oracle(case):
+def test_seeded_shapes_vs_oracle(case, family):
     B, N, D, M, K, d_out, bias, spread, q_gain = case
+    require_family(family, B, N, D, M)
     p = O.build_head(D, M, K, d_out=d_out, qkv_bias=bias, seed=0)
     p.cls_token = p.cls_token * q_gain
     x = O.synthetic_tokens(B, N, D, seed=1234, spread=spread)
@@ -130,6 +157,7 @@ def test_seeded_shapes_vs_oracle(case):
     head_t = head_from_params(p, K)
     tr = E.EPHeadTrainer(head_t, B, N, lr=0.0, use_graph=False)
     tr.train_step(xg, yg)
+    assert E._lib.load().ep_last_kernel_family() == family
     if B > 1:
         close(tr.logits, ref["logits"], TOL_FWD, "trainer logits")
         for k, grad in zip([n for n, _ in head_t.named_parameters()], tr.grads):
