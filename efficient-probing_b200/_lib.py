@@ -24,6 +24,7 @@ _SIGNATURES = {
     "ep_set_kernel_mode": (c_int, [c_int]),
     "ep_last_kernel_family": (c_int, []),
     "ep_launch_count": (ctypes.c_ulonglong, []),
+    "ep_set_debug": (c_int, [c_int]),
     "ep_kernel_family_for": (c_int, [c_int] * 5),
     "ep_workspace_bytes": (c_size_t, [c_int] * 5),
     "ep_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 5 +
@@ -36,8 +37,10 @@ _SIGNATURES = {
     "ep_attention_maps": (c_int, [c_void_p, c_int, c_void_p, c_float] + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ep_bn_fwd": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int] + [c_void_p] * 7),
     "ep_bn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "ep_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "ep_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ep_linear_workspace_bytes": (c_size_t, [c_int] * 3),
+    "ep_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ep_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_size_t, c_void_p]),
     "ep_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ep_lars_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -3,9 +3,12 @@
 #include "ep_common.cuh"
 #include "ep_sm100.cuh"
 
+#include <algorithm>
+
 using namespace ep;
 
 unsigned long long ep::g_launch_count = 0;
+namespace ep { extern int g_debug; }
 static int g_kernel_mode = 0;                 // 0 auto, 1 general, 2 tcgen05
 static thread_local int t_last_family = 0;
 
@@ -38,6 +41,7 @@ extern "C" int ep_set_kernel_mode(int mode) {
   return 0;
 }
 extern "C" int ep_last_kernel_family(void) { return t_last_family; }
+extern "C" int ep_set_debug(int flags) { ep::g_debug = flags; return 0; }
 extern "C" int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M) {
   if (g_kernel_mode == 1) return 1;
   return sm100_supported(x_dtype, B, N, D, M) ? 2 : (g_kernel_mode == 2 ? 0 : 1);
@@ -45,12 +49,18 @@ extern "C" int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M) {
 extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count; }
 
 namespace {
-struct Ws {                      // backward workspace layout
-  size_t dP, delta, slots, sm100, total;
+struct Ws {                      // workspace layout
+  size_t dP, delta, slots, sm100, w_r, g_r, total;
 };
+// The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
+// CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
+bool use_tc() { return gemm_tc_available() && !(ep::g_debug & 128); }
+int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
+  w.w_r = off;   off += align_up((size_t)D * D * sizeof(float), 256);       // >= (D/d_out) * D
+  w.g_r = off;   off += align_up((size_t)B * D * sizeof(float), 256);       // >= B * D/d_out
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
   w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
   w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
@@ -102,6 +112,15 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   if (rc) return rc;
   // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
   const int Dp = D / d_out, c = Dp / M;
+  if (use_tc()) {
+    float* w_r = (float*)((char*)workspace + w.w_r);
+    if ((rc = launch_round_tf32(v_w, w_r, (size_t)Dp * D, s))) return rc;
+    TcSide A{P, (unsigned long long)D, (unsigned long long)M, (unsigned long long)B, (unsigned long long)D,
+             (unsigned long long)M * D, TC_KMAJOR, 1, 1};
+    TcSide Bm{w_r, (unsigned long long)D, (unsigned long long)c, (unsigned long long)M, (unsigned long long)D,
+              (unsigned long long)c * D, TC_KMAJOR, 0, 1};
+    return tc_gemm(A, Bm, B, c, D, M, round_nt(c), out, Dp, 1, c, v_b, c, 0, s);
+  }
   GemmDesc g{};
   g.A = P; g.B = v_w; g.C = out; g.bias = v_b;
   g.I = B; g.J = c; g.K = D; g.Z = M;
@@ -123,6 +142,28 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
   float* delta = (float*)((char*)workspace + w.delta);
   const int Dp = D / d_out, c = Dp / M;
   int rc;
+  if (use_tc()) {
+    float* w_r = (float*)((char*)workspace + w.w_r);
+    float* g_r = (float*)((char*)workspace + w.g_r);
+    if ((rc = launch_round_tf32(v_w, w_r, (size_t)Dp * D, s))) return rc;
+    if ((rc = launch_round_tf32(g_out, g_r, (size_t)B * Dp, s))) return rc;
+    {  // d_v_w^T tile: rows d, cols j, contraction over the batch
+      TcSide A{P, (unsigned long long)D, (unsigned long long)M, (unsigned long long)B, (unsigned long long)D,
+               (unsigned long long)M * D, TC_MNMAJOR, 1, 1};
+      TcSide Bm{g_r, (unsigned long long)c, (unsigned long long)M, (unsigned long long)B, (unsigned long long)c,
+                (unsigned long long)Dp, TC_MNMAJOR, 1, 1};
+      if ((rc = tc_gemm(A, Bm, D, c, B, M, round_nt(c), d_v_w, 1, D, (long long)c * D, nullptr, 0, 0, s))) return rc;
+    }
+    if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
+    {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]
+      TcSide A{g_r, (unsigned long long)c, (unsigned long long)M, (unsigned long long)B, (unsigned long long)c,
+               (unsigned long long)Dp, TC_KMAJOR, 1, 1};
+      TcSide Bm{w_r, (unsigned long long)D, (unsigned long long)c, (unsigned long long)M, (unsigned long long)D,
+                (unsigned long long)c * D, TC_MNMAJOR, 0, 1};
+      if ((rc = tc_gemm(A, Bm, B, D, c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
+    }
+    return launch_rowdot(dP, P, (long long)B * M, D, delta, s);
+  }
   {  // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]
     GemmDesc g{};
     g.A = g_out; g.B = P; g.C = d_v_w;
@@ -195,37 +236,88 @@ extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_to
                      (cudaStream_t)stream);
 }
 
+extern "C" size_t ep_linear_workspace_bytes(int B, int F, int K) {
+  if (B <= 0 || F <= 0 || K <= 0) return 0;
+  return align_up((size_t)K * F * 4, 256) + align_up((size_t)B * F * 4, 256) + align_up((size_t)B * K * 4, 256);
+}
+namespace {
+struct LinWs { float *w_r, *y_r, *d_r; };
+bool lin_ws(void* ws, size_t bytes, int B, int F, int K, LinWs* o) {
+  if (!ws || bytes < ep_linear_workspace_bytes(B, F, K)) return false;
+  char* p = (char*)ws;
+  o->w_r = (float*)p; p += align_up((size_t)K * F * 4, 256);
+  o->y_r = (float*)p; p += align_up((size_t)B * F * 4, 256);
+  o->d_r = (float*)p;
+  return true;
+}
+}  // namespace
+
 extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
-                             void* stream) {
+                             void* workspace, size_t workspace_bytes, void* stream) {
   if (!y || !W || !logits) return EP_ERR_NULL;
+  if (B <= 0 || F <= 0 || K <= 0) return EP_ERR_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  LinWs lw;
+  if (use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw)) {
+    int rc;
+    if ((rc = launch_round_tf32(W, lw.w_r, (size_t)K * F, s))) return rc;
+    if ((rc = launch_round_tf32(y, lw.y_r, (size_t)B * F, s))) return rc;
+    TcSide A{lw.y_r, (unsigned long long)F, (unsigned long long)B, 1ull, (unsigned long long)F,
+             (unsigned long long)B * F, TC_KMAJOR, 0, 1};
+    TcSide Bm{lw.w_r, (unsigned long long)F, (unsigned long long)K, 1ull, (unsigned long long)F,
+              (unsigned long long)K * F, TC_KMAJOR, 0, 1};
+    return tc_gemm(A, Bm, B, K, F, 1, 128, logits, K, 1, 0, b, 0, 0, s);
+  }
   GemmDesc g{};
   g.A = y; g.B = W; g.C = logits; g.bias = b;
   g.I = B; g.J = K; g.K = F; g.Z = 1;
   g.a_i = F; g.a_k = 1; g.b_k = 1; g.b_j = F; g.c_i = K; g.c_j = 1;
-  return launch_gemm_v0(g, (cudaStream_t)stream);
+  return launch_gemm_v0(g, s);
 }
 
 extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* W, int B, int F, int K, float* dW,
-                             float* db, float* dy, void* stream) {
+                             float* db, float* dy, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dlogits) return EP_ERR_NULL;
+  if (B <= 0 || F <= 0 || K <= 0) return EP_ERR_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  LinWs lw;
+  const bool tc = use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw);
+  if (tc && (rc = launch_round_tf32(dlogits, lw.d_r, (size_t)B * K, s))) return rc;
   if (dW) {
     if (!y) return EP_ERR_NULL;
-    GemmDesc g{};
-    g.A = dlogits; g.B = y; g.C = dW;
-    g.I = K; g.J = F; g.K = B; g.Z = 1;
-    g.a_i = 1; g.a_k = K; g.b_k = F; g.b_j = 1; g.c_i = F; g.c_j = 1;
-    if ((rc = launch_gemm_v0(g, s))) return rc;
+    if (tc) {                      // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: both operands MN-major
+      if ((rc = launch_round_tf32(y, lw.y_r, (size_t)B * F, s))) return rc;
+      TcSide A{lw.d_r, (unsigned long long)K, (unsigned long long)B, 1ull, (unsigned long long)K,
+               (unsigned long long)B * K, TC_MNMAJOR, 0, 1};
+      TcSide Bm{lw.y_r, (unsigned long long)F, (unsigned long long)B, 1ull, (unsigned long long)F,
+                (unsigned long long)B * F, TC_MNMAJOR, 0, 1};
+      if ((rc = tc_gemm(A, Bm, K, F, B, 1, 128, dW, F, 1, 0, nullptr, 0, 0, s))) return rc;
+    } else {
+      GemmDesc g{};
+      g.A = dlogits; g.B = y; g.C = dW;
+      g.I = K; g.J = F; g.K = B; g.Z = 1;
+      g.a_i = 1; g.a_k = K; g.b_k = F; g.b_j = 1; g.c_i = F; g.c_j = 1;
+      if ((rc = launch_gemm_v0(g, s))) return rc;
+    }
   }
   if (db && (rc = launch_colsum(dlogits, B, K, db, s))) return rc;
   if (dy) {
     if (!W) return EP_ERR_NULL;
-    GemmDesc g{};
-    g.A = dlogits; g.B = W; g.C = dy;
-    g.I = B; g.J = F; g.K = K; g.Z = 1;
-    g.a_i = K; g.a_k = 1; g.b_k = F; g.b_j = 1; g.c_i = F; g.c_j = 1;
-    if ((rc = launch_gemm_v0(g, s))) return rc;
+    if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: A K-major, B MN-major
+      if ((rc = launch_round_tf32(W, lw.w_r, (size_t)K * F, s))) return rc;
+      TcSide A{lw.d_r, (unsigned long long)K, (unsigned long long)B, 1ull, (unsigned long long)K,
+               (unsigned long long)B * K, TC_KMAJOR, 0, 1};
+      TcSide Bm{lw.w_r, (unsigned long long)F, (unsigned long long)K, 1ull, (unsigned long long)F,
+                (unsigned long long)K * F, TC_MNMAJOR, 0, 1};
+      if ((rc = tc_gemm(A, Bm, B, F, K, 1, 128, dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
+    } else {
+      GemmDesc g{};
+      g.A = dlogits; g.B = W; g.C = dy;
+      g.I = B; g.J = F; g.K = K; g.Z = 1;
+      g.a_i = K; g.a_k = 1; g.b_k = F; g.b_j = 1; g.c_i = F; g.c_j = 1;
+      if ((rc = launch_gemm_v0(g, s))) return rc;
+    }
   }
   return 0;
 }

@@ -26,6 +26,14 @@ constexpr int kNumSMs = 148;
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// round-to-nearest fp32 -> tf32 (10-bit mantissa): operands of the TF32 tensor-core GEMMs are stored
+// pre-rounded so that the hardware's truncation of the low bits is exact (no bias)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -67,6 +75,22 @@ struct GemmDesc {      // C[z][i][j] = sum_k A[z][i][k] * B[z][k][j] (+ bias[z][
 int launch_gemm_v0(const GemmDesc& g, cudaStream_t s);
 int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s);            // out[j] = sum_i a[i][j]
 int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s);  // out[i] = a[i].b[i]
+
+// TF32 tensor-core GEMM (ep_gemm_sm100.cu)
+struct GemmTC;
+bool gemm_tc_available();
+int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s);
+// C[z][i][j] = sum_k A.. B..; see ep_api.cu for the operand descriptions
+enum TcOperand { TC_KMAJOR = 0, TC_MNMAJOR = 1 };
+struct TcSide {            // one operand as a 3-D fp32 tensor (d0 contiguous) and how tiles index it
+  const float* base;
+  unsigned long long d0, d1, d2, s1, s2;   // sizes and element strides of dims 1, 2
+  int mn_major;            // 0: d0 is the contraction index; 1: d0 is the output (row/col) index
+  int swap;                // 0: dim1 = rows-or-k, dim2 = batch; 1: dim1 = batch, dim2 = rows-or-k
+  int zdiv;                // batch coordinate = z / zdiv
+};
+int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,
+            long long c_col, long long c_z, const float* bias, long long bias_z, int round_out, cudaStream_t s);
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 float* P, float* S_out, float* rowmax, float* rowsum, float* attn, cudaStream_t s);

@@ -1,0 +1,250 @@
+// TF32 tensor-core GEMM (tcgen05.mma kind::tf32, fp32 operands straight from global memory through TMA,
+// fp32 accumulate in TMEM) for the small dense contractions of the EP head:
+//   value projection of the pooled tokens and its two gradients (batched over the M queries),
+//   the classifier (probe_heads.py:76) and its two gradients.
+// One CTA computes one 128 x NT output tile of one batch entry: warp 0 = TMA producer, warp 1 = MMA
+// issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Either operand may be K-major (contraction index contiguous in memory) or MN-major (output index
+// contiguous); the same 128-byte-swizzled shared-memory bytes serve both through the descriptor's
+// major bit, so no operand is ever transposed or converted on the way.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "ep_ptx.cuh"
+#include "ep_common.cuh"
+
+namespace ep {
+using namespace ptx;
+
+constexpr int kGK = 32;                       // contraction elements per stage (one 128-byte swizzle row of fp32)
+constexpr int kGStages = 4;
+
+struct GemmTC {
+  int I, J, K;                                // C is I x J, contraction K
+  int NT;                                     // column tile (multiple of 32, <= 256)
+  int a_mn, b_mn;                             // operand majors
+  int a_swap, b_swap;                         // 0: coords (c0, row/k, z); 1: coords (c0, z, row/k)
+  int a_zdiv, b_zdiv;                         // operand batch coordinate = z / zdiv (broadcast over z when huge)
+  float* C; const float* bias;
+  long long c_row, c_col, c_z, bias_z;        // element strides of C and bias
+  int round_tf32;                             // round the stored result to tf32 (it feeds another TF32 GEMM)
+};
+
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTC g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 128u * 128u;                       // 128 rows (or 4 atoms x 32 k-rows) x 128 B
+  const uint32_t b_bytes = (uint32_t)g.NT * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + kGStages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kGStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kGStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kGStages + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tmem_cols = g.NT <= 32 ? 32 : g.NT <= 64 ? 64 : g.NT <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a); prefetch_tmap(&tm_b); }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int i0 = blockIdx.y * 128, j0 = blockIdx.x * g.NT, z = blockIdx.z;
+  const int nk = (g.K + kGK - 1) / kGK;
+  const int za = z / g.a_zdiv, zb = z / g.b_zdiv;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+        const int k0 = kc * kGK;
+        if (!g.a_mn) {                                         // [128 rows x 32 k]
+          tma_load_3d(dst, &tm_a, full_bar(s), k0, g.a_swap ? za : i0, g.a_swap ? i0 : za);
+        } else {                                               // 4 atoms of [32 k-rows x 32 mn]
+          for (int a = 0; a < 4; ++a)
+            tma_load_3d(dst + (uint32_t)a * 4096u, &tm_a, full_bar(s), i0 + 32 * a, g.a_swap ? za : k0,
+                        g.a_swap ? k0 : za);
+        }
+        const uint32_t bdst = dst + a_bytes;
+        if (!g.b_mn) {                                         // [NT rows x 32 k]
+          tma_load_3d(bdst, &tm_b, full_bar(s), k0, g.b_swap ? zb : j0, g.b_swap ? j0 : zb);
+        } else {
+          for (int a = 0; a < g.NT / 32; ++a)
+            tma_load_3d(bdst + (uint32_t)a * 4096u, &tm_b, full_bar(s), j0 + 32 * a, g.b_swap ? zb : k0,
+                        g.b_swap ? k0 : zb);
+        }
+        if (++s == kGStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, g.NT, g.a_mn, g.b_mn);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t asm_ = smem_base + (uint32_t)s * stage_bytes, bsm = asm_ + a_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                          // UMMA K = 8 fp32
+          const uint64_t ad = g.a_mn ? smem_desc_sw128(asm_ + 1024u * k, 4096, 1024)
+                                     : smem_desc_sw128(asm_ + 32u * k, 16, 1024);
+          const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + 1024u * k, 4096, 1024)
+                                     : smem_desc_sw128(bsm + 32u * k, 16, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+        }
+        umma_commit(empty_bar(s));
+        if (++s == kGStages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    const int wq = warp - 4;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int row = i0 + wq * 32 + lane;
+    const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16);
+    float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
+    const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
+    for (int c0 = 0; c0 < g.NT; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(acc + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (row < g.I) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = j0 + c0 + i;
+          if (col < g.J) {
+            float v = __uint_as_float(r[i]) + (bias ? __ldg(bias + col) : 0.f);
+            if (g.round_tf32) v = to_tf32(v);
+            crow[(long long)col * g.c_col] = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// elementwise round-to-nearest to tf32 (operands of the TF32 GEMMs are pre-rounded so that the tensor
+// core's truncation of the low mantissa bits is exact; an un-rounded operand would bias every product)
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+}  // namespace
+
+// fp32 tensor (d2, d1, d0) with element strides (s2, s1, 1); box (b2, b1, 32)
+int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                  uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return EP_ERR_DEVICE;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 4, s2 * 4};
+  cuuint32_t box[3] = {32, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : EP_ERR_UNSUPPORTED;
+}
+
+bool gemm_tc_available() { return encode_fn() != nullptr; }
+int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTC& g, int Z, cudaStream_t s);
+
+int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTC& g, int Z, cudaStream_t s) {
+  const size_t smem = (size_t)kGStages * (128 * 128 + (size_t)g.NT * 128) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((g.J + g.NT - 1) / g.NT, (g.I + 127) / 128, Z);
+  gemm_tf32_kernel<<<grid, 256, smem, s>>>(tm_a, tm_b, g);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int side_tmap(CUtensorMap* m, const TcSide& sd, int tile_rows) {
+  // K-major: box = 32 k x tile_rows rows; MN-major: box = 32 mn x 32 k-rows
+  const uint32_t r = sd.mn_major ? 32u : (uint32_t)tile_rows;
+  return make_tmap_f32(m, sd.base, sd.d0, sd.d1, sd.d2, sd.s1, sd.s2, sd.swap ? 1u : r, sd.swap ? r : 1u);
+}
+
+int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,
+            long long c_col, long long c_z, const float* bias, long long bias_z, int round_out, cudaStream_t s) {
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = side_tmap(&ta, A, 128))) return rc;
+  if ((rc = side_tmap(&tb, B, NT))) return rc;
+  GemmTC g{};
+  g.I = I; g.J = J; g.K = K; g.NT = NT;
+  g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
+  g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
+  g.C = C; g.bias = bias; g.c_row = c_row; g.c_col = c_col; g.c_z = c_z; g.bias_z = bias_z;
+  g.round_tf32 = round_out;
+  return launch_gemm_tc(ta, tb, g, Z, s);
+}
+
+int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s) {
+  const size_t n4 = n / 4;
+  round_tf32_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, 4 * kNumSMs), 256, 0, s>>>(src, dst, n4);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ep

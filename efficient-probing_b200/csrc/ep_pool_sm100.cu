@@ -21,12 +21,14 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 
 #include "ep_ptx.cuh"
 #include "ep_sm100.cuh"
 
 namespace ep {
 using namespace ptx;
+int g_debug = 0;        // developer knob (ep_set_debug): bit 0 = converter skips global loads, bit 1 = no P stores
 
 constexpr int kTileRows = 128;    // ks: token rows per MMA tile (UMMA M)
 constexpr int kChunkD = 64;       // bf16 elements per 128-byte swizzle row
@@ -45,7 +47,7 @@ struct KSParams {
 };
 
 struct KPParams {
-  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols;
+  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, debug;
   const float* src;      // (B, M, N): logits (mode 0) or dS (mode 1)
   const float* rmax;     // mode 0
   const float* rsum;     // mode 0
@@ -146,25 +148,49 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       mbar_wait(tfull_bar(buf), ((uint32_t)(it / p.nbuf)) & 1u);
       tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
+      // mode 1: lane l keeps the row statistics of queries l and 32 + l of this sample
+      float st_mx[2] = {0.f, 0.f}, st_inv[2] = {0.f, 0.f}, st_dl[2] = {0.f, 0.f};
+      if (kMode == 1) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = h * 32 + lane;
+          if (m < p.M) {
+            const size_t bm = (size_t)b * p.M + m;
+            st_mx[h] = __ldg(p.rmax + bm);
+            st_inv[h] = 1.f / __ldg(p.rsum + bm);
+            st_dl[h] = __ldg(p.delta + bm);
+          }
+        }
+      }
       for (int t = 0; t < gt; ++t) {
         const int n = (t0 + t) * kTileRows + wq * 32 + lane;
         for (int j0 = 0; j0 < p.J; j0 += 16) {
           uint32_t r[16];
           tmem_ld16(acc + (uint32_t)(t * p.J + j0), r);
-          tmem_ld_wait();
-          if (n < p.N) {
+          // issue the global loads of this 8-query batch before the first use (they are independent;
+          // otherwise the load -> exp -> store chain serialises on memory latency)
+          float sv[8];
+          if (kMode == 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int m = (j0 >> 1) + i;
-              if (m < p.M) {
-                float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
-                const size_t bm = (size_t)b * p.M + m;
-                if (kMode == 1) {
-                  const float a = __expf(p.S[bm * p.N + n] - p.rmax[bm]) / p.rsum[bm];
-                  v = a * (v - p.delta[bm]);
-                }
-                p.out[bm * p.N + n] = v;
+              const int m = min((j0 >> 1) + i, p.M - 1);
+              sv[i] = (n < p.N) ? __ldg(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = (j0 >> 1) + i;                     // warp-uniform
+            if (m < p.M) {
+              float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
+              if (kMode == 1) {
+                const int h = m >> 5, src = m & 31;
+                const float mx = __shfl_sync(0xffffffffu, st_mx[h], src);
+                const float inv = __shfl_sync(0xffffffffu, st_inv[h], src);
+                const float dl = __shfl_sync(0xffffffffu, st_dl[h], src);
+                v = __expf(sv[i] - mx) * inv * (v - dl);
               }
+              if (n < p.N) p.out[((size_t)b * p.M + m) * p.N + n] = v;
             }
           }
         }
@@ -259,8 +285,9 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t accum = (kMode == 0) ? (uint32_t)((kb | k) != 0) : (uint32_t)(!(first && kb == 0 && k == 0));
-              umma_f16(acc + (uint32_t)(sl * p.J), smem_desc_sw128(xsm + 2048u * k, kBrickBytes / 2, 1024),
-                       smem_desc_sw128(wsm + 32u * k, 16, 1024), idesc, accum);
+              if (!(p.debug & 16))
+                umma_f16(acc + (uint32_t)(sl * p.J), smem_desc_sw128(xsm + 2048u * k, kBrickBytes / 2, 1024),
+                         smem_desc_sw128(wsm + 32u * k, 16, 1024), idesc, accum);
             }
             umma_commit(xempty(xs));
             if (++xs == p.xslots) { xs = 0; xph ^= 1u; }
@@ -274,38 +301,64 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
       if (kMode == 1) umma_commit(afull(0));
     }
   } else if (warp >= 4 && warp < 8) {
-    // converter: fp32 (B, M, N) -> bf16 hi/lo K-major operand block [J rows x 64 tokens], 128B-swizzled
+    // converter: fp32 (B, M, N) -> bf16 hi/lo K-major operand block [J rows x 64 tokens], 128B-swizzled.
+    // Thread (t, half) converts token t for queries m = half + 2u, eight at a time (loads first).
     const int tid = threadIdx.x - 128;
     const int t = tid & 63, half = tid >> 6;
+    const int nm = (p.M - half + 1) / 2;
     int ws = 0;
     uint32_t wph = 0;
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x)
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      float mxl[2] = {0.f, 0.f};                             // lane l keeps rowmax of queries l and 32 + l
+      if (kMode == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          mxl[h] = (h * 32 + lane < p.M) ? __ldg(p.rmax + (size_t)b * p.M + h * 32 + lane) : 0.f;
+      }
       for (int kb = 0; kb < p.nkb; ++kb) {
-        mbar_wait(wempty(ws), wph ^ 1u);
-        uint8_t* wt = smem_gen + (wt_base - smem_base) + (size_t)ws * wt_bytes;
         const int n = kb * kTokBlock + t;
-        for (int m = half; m < p.M; m += 2) {
-          const size_t bm = (size_t)b * p.M + m;
-          float e = 0.f;
-          if (n < p.N) {
-            e = p.src[bm * p.N + n];
-            if (kMode == 0) e = __expf(e - p.rmax[bm]);
+        const float* row = p.src + ((size_t)b * p.M + half) * p.N + n;
+        const uint32_t col = (uint32_t)(t & 7) * 2u;
+        uint8_t* wt = smem_gen + (wt_base - smem_base) + (size_t)ws * wt_bytes;
+        bool waited = false;
+        for (int u0 = 0; u0 < nm; u0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            v[u] = (n < p.N && u0 + u < nm && !(p.debug & 1)) ? __ldg(row + (size_t)(2 * (u0 + u)) * p.N) : 0.f;
+          if (!waited) { mbar_wait(wempty(ws), wph ^ 1u); waited = true; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (u0 + u < nm && !(p.debug & 4)) {             // warp-uniform
+              const int m = half + 2 * (u0 + u);
+              float e = v[u];
+              if (kMode == 0) {
+                const float mx = __shfl_sync(0xffffffffu, mxl[m >> 5], m & 31);
+                e = (n < p.N) ? __expf(e - mx) : 0.f;
+              }
+              const __nv_bfloat16 hi = __float2bfloat16_rn(e);
+              const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
+              *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m, t >> 3) + col) = hi;
+              *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m + 1, t >> 3) + col) = lo;
+            }
           }
-          const __nv_bfloat16 hi = __float2bfloat16_rn(e);
-          const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
-          const uint32_t col = (uint32_t)(t & 7) * 2u;
-          *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m, t >> 3) + col) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m + 1, t >> 3) + col) = lo;
         }
         fence_proxy_async();
         mbar_arrive(wfull(ws));
         if (++ws == p.wslots) { ws = 0; wph ^= 1u; }
       }
+    }
   } else if (warp >= 8) {
     const int wq = warp - 8;
     auto drain = [&](int buf, int b) {
       const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
-      for (int sl = 0; sl < nsl; ++sl) {
+      float invl[2] = {1.f, 1.f};                            // lane l keeps 1/rowsum of queries l and 32 + l
+      if (kMode == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (h * 32 + lane < p.M) invl[h] = 1.f / __ldg(p.rsum + (size_t)b * p.M + h * 32 + lane);
+      }
+      for (int sl = 0; sl < ((p.debug & 8) ? 0 : nsl); ++sl) {
         const int d = d0 + sl * 128 + wq * 32 + lane;
         for (int j0 = 0; j0 < p.J; j0 += 16) {
           uint32_t r[16];
@@ -313,12 +366,12 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int m = (j0 >> 1) + i;
+            const int m = (j0 >> 1) + i;                     // warp-uniform
             if (m < p.M) {
               float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
               if (kMode == 0) {
-                v /= p.rsum[(size_t)b * p.M + m];
-                p.out[((size_t)b * p.M + m) * p.D + d] = v;
+                v = round_tf32(v * __shfl_sync(0xffffffffu, invl[m >> 5], m & 31));   // P feeds TF32 GEMMs
+                if (!(p.debug & 2)) p.out[((size_t)b * p.M + m) * p.D + d] = v;
               } else {
                 p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
               }
@@ -407,6 +460,25 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int npart
 // host side
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// developer aid (ep_set_debug bit 5): CUDA-event time of every kernel of one call, printed to stderr
+struct StageTimer {
+  bool on; cudaStream_t s; cudaEvent_t ev[12]; const char* name[12]; int n = 0;
+  StageTimer(cudaStream_t st) : on((g_debug & 32) != 0), s(st) { if (on) mark("start"); }
+  void mark(const char* nm) {
+    if (!on || n >= 12) return;
+    cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], s); name[n++] = nm;
+  }
+  ~StageTimer() {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, "[ep timing] %-18s %8.1f us\n", name[i], ms * 1e3f);
+    }
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+  }
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -525,13 +597,15 @@ int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const f
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTokBlock))) return rc;
   KPParams p{};
   p.B = B; p.N = N; p.D = D; p.M = M; p.J = pl.J; p.nkb = pl.nkb;
-  p.nsl = kMode == 0 ? pl.nsl_fwd : pl.nsl_bwd;
-  const int ysplit = kMode == 0 ? pl.ysplit_fwd : pl.ysplit_bwd;
+  const bool wide = (g_debug & 64) != 0;                      // experiment: forward with the backward's D split
+  p.nsl = (kMode == 0 && !wide) ? pl.nsl_fwd : pl.nsl_bwd;
+  const int ysplit = (kMode == 0 && !wide) ? pl.ysplit_fwd : pl.ysplit_bwd;
   p.xslots = pl.xslots; p.wslots = pl.wslots;
   p.bufcols = p.nsl * pl.J;
   p.nbuf = (kMode == 0 && 2 * p.bufcols <= 512) ? 2 : 1;
   p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
   p.src = src; p.rmax = rmax; p.rsum = rsum; p.out = out;
+  p.debug = g_debug;
   if ((rc = set_dyn_smem(kp_kernel<kMode>, pl.kp_smem))) return rc;
   const int gx = std::max(1, std::min(B, kNumSMs / ysplit));
   if (groups_out) *groups_out = gx;
@@ -560,14 +634,20 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   const Ws100 w = carve100(B, N, D, M, pl);
   __nv_bfloat16* qhl = (__nv_bfloat16*)((char*)ws + w.qhl);
   int rc;
+  StageTimer tm(s);
   split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
   EP_LAUNCH_CHECK();
+  tm.mark("split_q");
   if ((rc = launch_ks<0>(x, qhl, 0, B, N, D, M, pl, S, nullptr, nullptr, nullptr, nullptr, s))) return rc;
+  tm.mark("ks<0> logits");
   const long long rows = (long long)B * M;
   rowstats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, rows, N, rowmax, rowsum, attn);
   EP_LAUNCH_CHECK();
+  tm.mark("rowstats");
   if (P == nullptr) return 0;
-  return launch_kp<0>(x, B, N, D, M, pl, S, rowmax, rowsum, P, nullptr, s);
+  rc = launch_kp<0>(x, B, N, D, M, pl, S, rowmax, rowsum, P, nullptr, s);
+  tm.mark("kp<0> pool");
+  return rc;
 }
 
 int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int D, int M, const float* rowmax,
@@ -579,14 +659,19 @@ int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int
   float* dS = (float*)((char*)ws + w.dS);
   float* part = (float*)((char*)ws + w.part);
   int rc;
+  StageTimer tm(s);
   split_hilo_kernel<<<dim3(std::max(1, std::min(64, pl.J * D / 8 / 256)), B), 256, 0, s>>>(dP, 1.f, M, pl.J, D, dphl);
   EP_LAUNCH_CHECK();
+  tm.mark("split_dP");
   if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, dS, S, rowmax, rowsum, delta, s))) return rc;
+  tm.mark("ks<1> dS");
   int groups = 0;
   if ((rc = launch_kp<1>(x, B, N, D, M, pl, dS, nullptr, nullptr, part, &groups, s))) return rc;
+  tm.mark("kp<1> dq");
   const size_t n = (size_t)M * D;
   reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, groups, n, scale, d_cls);
   EP_LAUNCH_CHECK();
+  tm.mark("reduce");
   return 0;
 }
 

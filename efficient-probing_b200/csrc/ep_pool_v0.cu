@@ -133,7 +133,8 @@ pool_fwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, floa
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (mb + j < M)
-          *reinterpret_cast<float2*>(P + ((size_t)b * M + mb + j) * D + dd) = make_float2(acc[j][0], acc[j][1]);
+          *reinterpret_cast<float2*>(P + ((size_t)b * M + mb + j) * D + dd) =
+              make_float2(round_tf32(acc[j][0]), round_tf32(acc[j][1]));          // P feeds TF32 GEMMs
     }
   }
 }

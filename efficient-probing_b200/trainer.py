@@ -99,6 +99,7 @@ class EPHeadTrainer:
         self.hyper_host = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world]).pin_memory()
         self.lars_scratch = torch.empty(16, **f32)
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
+        self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
         self._cx, self._ct = self.x, self.targets           # the batch the next launch sequence reads
         self._registered = {}                               # (x ptr, targets ptr) -> (x, targets) kept alive
@@ -122,7 +123,8 @@ class EPHeadTrainer:
                                  bn.num_batches_tracked.data_ptr(), self.y.data_ptr(), self.save_mean.data_ptr(),
                                  self.save_invstd.data_ptr(), s), "ep_bn_fwd")
         _lib.check(lib.ep_linear_fwd(self.y.data_ptr(), fc.weight.data_ptr(), fc.bias.data_ptr(), B, Dp, K,
-                                     self.logits.data_ptr(), s), "ep_linear_fwd")
+                                     self.logits.data_ptr(), self.lin_ws.data_ptr(), self.lin_ws.numel(), s),
+                   "ep_linear_fwd")
 
     def _step_body(self):
         lib, s = self.lib, _lib.stream_ptr(self.dev)
@@ -134,8 +136,8 @@ class EPHeadTrainer:
                                      self.step_loss.data_ptr(), self.dlogits.data_ptr(), self.correct.data_ptr(), s),
                    "ep_ce_fwd_bwd")
         _lib.check(lib.ep_linear_bwd(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
-                                     self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), self.dy.data_ptr(), s),
-                   "ep_linear_bwd")
+                                     self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), self.dy.data_ptr(),
+                                     self.lin_ws.data_ptr(), self.lin_ws.numel(), s), "ep_linear_bwd")
         _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
                                  self.dout.data_ptr(), s), "ep_bn_bwd")
         d_vb = self.g["v_b"].data_ptr() if pool.v.bias is not None else None

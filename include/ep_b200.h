@@ -50,6 +50,8 @@ int ep_device_check(void);
 int ep_set_kernel_mode(int mode);
 /* Which family the last ep_fwd/ep_bwd call on this thread used (1 = general, 2 = tcgen05). */
 int ep_last_kernel_family(void);
+/* Developer knob for performance experiments (results are WRONG when non-zero); 0 in normal use. */
+int ep_set_debug(int flags);
 /* Which family ep_fwd/ep_bwd would use for this shape under the current mode (0 = none: forced tcgen05
  * but unsupported). */
 int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M);
@@ -107,11 +109,15 @@ int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum, int train
 /* dh = invstd * (dy - mean_b(dy) - y * mean_b(dy*y)). */
 int ep_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, void* stream);
 
-/* nn.Linear(F, K, bias=True) -- probe_heads.py:76.  logits = y @ W^T + b. */
-int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits, void* stream);
+/* nn.Linear(F, K, bias=True) -- probe_heads.py:76.  logits = y @ W^T + b.
+ * With a workspace of ep_linear_workspace_bytes() the contraction runs on the tensor cores in TF32
+ * (operands rounded to nearest tf32, fp32 accumulate); with workspace == NULL on the CUDA cores in fp32. */
+size_t ep_linear_workspace_bytes(int B, int F, int K);
+int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
+                  void* workspace, size_t workspace_bytes, void* stream);
 /* dW = dlogits^T @ y (K, F); db = sum_b dlogits (K,); dy = dlogits @ W (B, F).  Any output may be NULL. */
 int ep_linear_bwd(const float* dlogits, const float* y, const float* W, int B, int F, int K,
-                  float* dW, float* db, float* dy, void* stream);
+                  float* dW, float* db, float* dy, void* workspace, size_t workspace_bytes, void* stream);
 
 /* nn.CrossEntropyLoss() (mean) forward + backward in one pass -- main_linprobe.py:589, engine_finetune.py:62.
  * loss_sum[0] += sum_b nll_b * loss_scale  (caller zeroes it; loss_scale = 1/B gives the mean);
