@@ -50,7 +50,7 @@ extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count;
 
 namespace {
 struct Ws {                      // workspace layout
-  size_t dP, delta, slots, sm100, w_r, g_r, total;
+  size_t dP, delta, slots, sm100, w_r, w_t, g_r, total;
 };
 // The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
@@ -60,6 +60,7 @@ Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
   w.w_r = off;   off += align_up((size_t)D * D * sizeof(float), 256);       // >= (D/d_out) * D
+  w.w_t = off;   off += align_up((size_t)D * D * sizeof(float), 256);       // per-query transposed copy
   w.g_r = off;   off += align_up((size_t)B * D * sizeof(float), 256);       // >= B * D/d_out
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
   w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
@@ -143,23 +144,19 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
   const int Dp = D / d_out, c = Dp / M;
   int rc;
   if (use_tc()) {
-    float* w_r = (float*)((char*)workspace + w.w_r);
     float* g_r = (float*)((char*)workspace + w.g_r);
-    if ((rc = launch_round_tf32(v_w, w_r, (size_t)Dp * D, s))) return rc;
     if ((rc = launch_round_tf32(g_out, g_r, (size_t)B * Dp, s))) return rc;
-    {  // d_v_w^T tile: rows d, cols j, contraction over the batch
-      TcSide A{P, (unsigned long long)D, (unsigned long long)M, (unsigned long long)B, (unsigned long long)D,
-               (unsigned long long)M * D, TC_MNMAJOR, 1, 1};
-      TcSide Bm{g_r, (unsigned long long)c, (unsigned long long)M, (unsigned long long)B, (unsigned long long)c,
-                (unsigned long long)Dp, TC_MNMAJOR, 1, 1};
-      if ((rc = tc_gemm(A, Bm, D, c, B, M, round_nt(c), d_v_w, 1, D, (long long)c * D, nullptr, 0, 0, s))) return rc;
-    }
+    // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch, both operands
+    // batch-major -> TF32 mma.sync "TN" kernel reading them as they lie
+    if ((rc = launch_gemm_tn(g_out, P, d_v_w, c, D, B, M, Dp, (long long)M * D, D, c, D, (long long)c * D, s))) return rc;
     if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
-    {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]
+    {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05 with a per-query transposed weight copy
+      float* w_t = (float*)((char*)workspace + w.w_t);            // w_t[m][d][j] = tf32(v_w[m*c + j][d])
+      if ((rc = launch_transpose_round(v_w, w_t, c, D, M, (long long)c * D, (long long)c * D, s))) return rc;
       TcSide A{g_r, (unsigned long long)c, (unsigned long long)M, (unsigned long long)B, (unsigned long long)c,
                (unsigned long long)Dp, TC_KMAJOR, 1, 1};
-      TcSide Bm{w_r, (unsigned long long)D, (unsigned long long)c, (unsigned long long)M, (unsigned long long)D,
-                (unsigned long long)c * D, TC_MNMAJOR, 0, 1};
+      TcSide Bm{w_t, (unsigned long long)c, (unsigned long long)D, (unsigned long long)M, (unsigned long long)c,
+                (unsigned long long)c * D, TC_KMAJOR, 0, 1};
       if ((rc = tc_gemm(A, Bm, B, D, c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
     }
     return launch_rowdot(dP, P, (long long)B * M, D, delta, s);
@@ -238,14 +235,15 @@ extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_to
 
 extern "C" size_t ep_linear_workspace_bytes(int B, int F, int K) {
   if (B <= 0 || F <= 0 || K <= 0) return 0;
-  return align_up((size_t)K * F * 4, 256) + align_up((size_t)B * F * 4, 256) + align_up((size_t)B * K * 4, 256);
+  return 2 * align_up((size_t)K * F * 4, 256) + align_up((size_t)B * F * 4, 256) + align_up((size_t)B * K * 4, 256);
 }
 namespace {
-struct LinWs { float *w_r, *y_r, *d_r; };
+struct LinWs { float *w_r, *w_t, *y_r, *d_r; };
 bool lin_ws(void* ws, size_t bytes, int B, int F, int K, LinWs* o) {
   if (!ws || bytes < ep_linear_workspace_bytes(B, F, K)) return false;
   char* p = (char*)ws;
   o->w_r = (float*)p; p += align_up((size_t)K * F * 4, 256);
+  o->w_t = (float*)p; p += align_up((size_t)K * F * 4, 256);
   o->y_r = (float*)p; p += align_up((size_t)B * F * 4, 256);
   o->d_r = (float*)p;
   return true;
@@ -286,13 +284,8 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   if (tc && (rc = launch_round_tf32(dlogits, lw.d_r, (size_t)B * K, s))) return rc;
   if (dW) {
     if (!y) return EP_ERR_NULL;
-    if (tc) {                      // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: both operands MN-major
-      if ((rc = launch_round_tf32(y, lw.y_r, (size_t)B * F, s))) return rc;
-      TcSide A{lw.d_r, (unsigned long long)K, (unsigned long long)B, 1ull, (unsigned long long)K,
-               (unsigned long long)B * K, TC_MNMAJOR, 0, 1};
-      TcSide Bm{lw.y_r, (unsigned long long)F, (unsigned long long)B, 1ull, (unsigned long long)F,
-                (unsigned long long)B * F, TC_MNMAJOR, 0, 1};
-      if ((rc = tc_gemm(A, Bm, K, F, B, 1, 128, dW, F, 1, 0, nullptr, 0, 0, s))) return rc;
+    if (tc) {                      // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: batch-major operands, "TN" kernel
+      if ((rc = launch_gemm_tn(dlogits, y, dW, K, F, B, 1, K, F, F, 0, 0, 0, s))) return rc;
     } else {
       GemmDesc g{};
       g.A = dlogits; g.B = y; g.C = dW;
@@ -304,12 +297,12 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   if (db && (rc = launch_colsum(dlogits, B, K, db, s))) return rc;
   if (dy) {
     if (!W) return EP_ERR_NULL;
-    if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: A K-major, B MN-major
-      if ((rc = launch_round_tf32(W, lw.w_r, (size_t)K * F, s))) return rc;
+    if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05 with a transposed weight copy
+      if ((rc = launch_transpose_round(W, lw.w_t, K, F, 1, 0, 0, s))) return rc;     // w_t[f][k]
       TcSide A{lw.d_r, (unsigned long long)K, (unsigned long long)B, 1ull, (unsigned long long)K,
                (unsigned long long)B * K, TC_KMAJOR, 0, 1};
-      TcSide Bm{lw.w_r, (unsigned long long)F, (unsigned long long)K, 1ull, (unsigned long long)F,
-                (unsigned long long)K * F, TC_MNMAJOR, 0, 1};
+      TcSide Bm{lw.w_t, (unsigned long long)K, (unsigned long long)F, 1ull, (unsigned long long)K,
+                (unsigned long long)K * F, TC_KMAJOR, 0, 1};
       if ((rc = tc_gemm(A, Bm, B, F, K, 1, 128, dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
     } else {
       GemmDesc g{};

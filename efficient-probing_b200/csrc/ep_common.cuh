@@ -92,6 +92,11 @@ struct TcSide {            // one operand as a 3-D fp32 tensor (d0 contiguous) a
 int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,
             long long c_col, long long c_z, const float* bias, long long bias_z, int round_out, cudaStream_t s);
 
+int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K, int Z, long long lda, long long ldb,
+                   long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s);
+int launch_transpose_round(const float* src, float* dst, int R, int Cc, int Z, long long src_z, long long dst_z,
+                           cudaStream_t s);
+
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 float* P, float* S_out, float* rowmax, float* rowsum, float* attn, cudaStream_t s);
 int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,

@@ -112,3 +112,148 @@ int launch_rowdot(const float* a, const float* b, long long rows, int cols, floa
 }
 
 }  // namespace ep
+
+// ------------------------------------------------------------------------------------------------
+// C[z][i][j] = sum_k A[z][k][i] * B[z][k][j]  ("TN": both operands have the contraction index as their
+// slow dimension -- weight gradients, contraction over the batch).  TF32 mma.sync m16n8k8 with the
+// operands rounded to tf32 in registers, fp32 accumulate; tiles are staged through shared memory as
+// they lie in global memory, so no transposed copy of the (large) activation operand is needed.
+// ------------------------------------------------------------------------------------------------
+namespace ep {
+
+constexpr int TN_BI = 64, TN_BJ = 128, TN_BK = 16, TN_LDA = TN_BI + 8, TN_LDB = TN_BJ + 8;
+
+__device__ __forceinline__ uint32_t f2tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+struct GemmTN {
+  const float* A; const float* B; float* C;
+  int I, J, K;
+  long long lda, ldb, ldc, a_z, b_z, c_z;
+};
+
+__global__ void __launch_bounds__(256) gemm_tn_mma_kernel(GemmTN g) {
+  __shared__ __align__(16) float As[2][TN_BK][TN_LDA];
+  __shared__ __align__(16) float Bs[2][TN_BK][TN_LDB];
+  const int z = blockIdx.z;
+  const float* A = g.A + (long long)z * g.a_z;
+  const float* B = g.B + (long long)z * g.b_z;
+  float* C = g.C + (long long)z * g.c_z;
+  const int i0 = blockIdx.y * TN_BI, j0 = blockIdx.x * TN_BJ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wi = (warp >> 2) * 32, wj = (warp & 3) * 32;      // warp tile origin inside the CTA tile
+  const int gq = lane >> 2, tq = lane & 3;
+  float acc[2][4][4] = {};
+
+  auto load_stage = [&](int st, int k0) {
+    // A chunk: 16 k x 64 i = 256 float4; B chunk: 16 k x 128 j = 512 float4
+    for (int e = threadIdx.x; e < 256; e += 256) {
+      const int k = e >> 4, i = (e & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < g.K && i0 + i < g.I) {
+        const float* p = A + (long long)(k0 + k) * g.lda + i0 + i;
+        if (i0 + i + 3 < g.I) v = __ldg(reinterpret_cast<const float4*>(p));
+        else { v.x = __ldg(p); if (i0 + i + 1 < g.I) v.y = __ldg(p + 1); if (i0 + i + 2 < g.I) v.z = __ldg(p + 2); }
+      }
+      *reinterpret_cast<float4*>(&As[st][k][i]) = v;
+    }
+    for (int e = threadIdx.x; e < 512; e += 256) {
+      const int k = e >> 5, j = (e & 31) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < g.K && j0 + j < g.J) {
+        const float* p = B + (long long)(k0 + k) * g.ldb + j0 + j;
+        if (j0 + j + 3 < g.J) v = __ldg(reinterpret_cast<const float4*>(p));
+        else { v.x = __ldg(p); if (j0 + j + 1 < g.J) v.y = __ldg(p + 1); if (j0 + j + 2 < g.J) v.z = __ldg(p + 2); }
+      }
+      *reinterpret_cast<float4*>(&Bs[st][k][j]) = v;
+    }
+  };
+
+  const int nk = (g.K + TN_BK - 1) / TN_BK;
+  load_stage(0, 0);
+  __syncthreads();
+  for (int kc = 0; kc < nk; ++kc) {
+    const int st = kc & 1;
+    if (kc + 1 < nk) load_stage(st ^ 1, (kc + 1) * TN_BK);
+#pragma unroll
+    for (int kk = 0; kk < TN_BK; kk += 8) {
+      uint32_t a[2][4], b[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int i = wi + mi * 16 + gq;
+        a[mi][0] = f2tf32(As[st][kk + tq][i]);
+        a[mi][1] = f2tf32(As[st][kk + tq][i + 8]);
+        a[mi][2] = f2tf32(As[st][kk + tq + 4][i]);
+        a[mi][3] = f2tf32(As[st][kk + tq + 4][i + 8]);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int j = wj + ni * 8 + gq;
+        b[ni][0] = f2tf32(Bs[st][kk + tq][j]);
+        b[ni][1] = f2tf32(Bs[st][kk + tq + 4][j]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          asm volatile(
+              "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[mi][ni][0]), "+f"(acc[mi][ni][1]), "+f"(acc[mi][ni][2]), "+f"(acc[mi][ni][3])
+              : "r"(a[mi][0]), "r"(a[mi][1]), "r"(a[mi][2]), "r"(a[mi][3]), "r"(b[ni][0]), "r"(b[ni][1]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = i0 + wi + mi * 16 + gq + h * 8;
+        const int j = j0 + wj + ni * 8 + tq * 2;
+        if (i < g.I) {
+          if (j < g.J) C[(long long)i * g.ldc + j] = acc[mi][ni][2 * h];
+          if (j + 1 < g.J) C[(long long)i * g.ldc + j + 1] = acc[mi][ni][2 * h + 1];
+        }
+      }
+}
+
+int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K, int Z, long long lda, long long ldb,
+                   long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s) {
+  if (I <= 0 || J <= 0 || K <= 0 || Z <= 0) return EP_ERR_SHAPE;
+  if ((lda | ldb | a_z | b_z) & 3) return EP_ERR_ALIGN;
+  GemmTN g{A, B, C, I, J, K, lda, ldb, ldc, a_z, b_z, c_z};
+  dim3 grid((J + TN_BJ - 1) / TN_BJ, (I + TN_BI - 1) / TN_BI, Z);
+  gemm_tn_mma_kernel<<<grid, 256, 0, s>>>(g);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[z][c][r] = tf32(src[z][r][c]): K-major (transposed) copy of a weight block for the tcgen05 GEMMs
+__global__ void transpose_round_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc,
+                                       long long src_z, long long dst_z) {
+  __shared__ float tile[32][33];
+  const float* s = src + (long long)blockIdx.z * src_z;
+  float* d = dst + (long long)blockIdx.z * dst_z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? s[(long long)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) d[(long long)c * R + r] = round_tf32(tile[threadIdx.x][i]);
+  }
+}
+int launch_transpose_round(const float* src, float* dst, int R, int Cc, int Z, long long src_z, long long dst_z,
+                           cudaStream_t s) {
+  transpose_round_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32, Z), dim3(32, 8), 0, s>>>(src, dst, R, Cc, src_z, dst_z);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ep
