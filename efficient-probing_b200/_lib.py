@@ -23,6 +23,7 @@ _SIGNATURES = {
     "ep_device_check": (c_int, []),
     "ep_set_kernel_mode": (c_int, [c_int]),
     "ep_last_kernel_family": (c_int, []),
+    "ep_set_gemm_mode": (c_int, [c_int]),
     "ep_launch_count": (ctypes.c_ulonglong, []),
     "ep_set_debug": (c_int, [c_int]),
     "ep_kernel_family_for": (c_int, [c_int] * 5),

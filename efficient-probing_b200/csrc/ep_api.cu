@@ -9,6 +9,7 @@ using namespace ep;
 
 unsigned long long ep::g_launch_count = 0;
 namespace ep { extern int g_debug; }
+static int g_gemm_mode = 0;                   // 0 = TF32 tensor cores, 1 = fp32 CUDA cores
 static int g_kernel_mode = 0;                 // 0 auto, 1 general, 2 tcgen05
 static thread_local int t_last_family = 0;
 
@@ -41,6 +42,11 @@ extern "C" int ep_set_kernel_mode(int mode) {
   return 0;
 }
 extern "C" int ep_last_kernel_family(void) { return t_last_family; }
+extern "C" int ep_set_gemm_mode(int mode) {
+  if (mode < 0 || mode > 1) return EP_ERR_SHAPE;
+  g_gemm_mode = mode;
+  return 0;
+}
 extern "C" int ep_set_debug(int flags) { ep::g_debug = flags; return 0; }
 extern "C" int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M) {
   if (g_kernel_mode == 1) return 1;
@@ -54,7 +60,7 @@ struct Ws {                      // workspace layout
 };
 // The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
-bool use_tc() { return gemm_tc_available() && !(ep::g_debug & 128); }
+bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !(ep::g_debug & 128); }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 Ws carve(int B, int N, int D, int M) {
   Ws w;
@@ -113,7 +119,7 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   if (rc) return rc;
   // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
   const int Dp = D / d_out, c = Dp / M;
-  if (use_tc()) {
+  if (use_tc() && c % 4 == 0) {
     float* w_r = (float*)((char*)workspace + w.w_r);
     if ((rc = launch_round_tf32(v_w, w_r, (size_t)Dp * D, s))) return rc;
     TcSide A{P, (unsigned long long)D, (unsigned long long)M, (unsigned long long)B, (unsigned long long)D,
@@ -143,23 +149,30 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
   float* delta = (float*)((char*)workspace + w.delta);
   const int Dp = D / d_out, c = Dp / M;
   int rc;
-  if (use_tc()) {
+  StageTimer tm(s);
+  if (use_tc() && c % 4 == 0) {
     float* g_r = (float*)((char*)workspace + w.g_r);
     if ((rc = launch_round_tf32(g_out, g_r, (size_t)B * Dp, s))) return rc;
+    tm.mark("round g");
     // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch, both operands
     // batch-major -> TF32 mma.sync "TN" kernel reading them as they lie
     if ((rc = launch_gemm_tn(g_out, P, d_v_w, c, D, B, M, Dp, (long long)M * D, D, c, D, (long long)c * D, s))) return rc;
+    tm.mark("dW tn-gemm");
     if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
     {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05 with a per-query transposed weight copy
       float* w_t = (float*)((char*)workspace + w.w_t);            // w_t[m][d][j] = tf32(v_w[m*c + j][d])
       if ((rc = launch_transpose_round(v_w, w_t, c, D, M, (long long)c * D, (long long)c * D, s))) return rc;
+      tm.mark("transpose W");
       TcSide A{g_r, (unsigned long long)c, (unsigned long long)M, (unsigned long long)B, (unsigned long long)c,
                (unsigned long long)Dp, TC_KMAJOR, 1, 1};
       TcSide Bm{w_t, (unsigned long long)c, (unsigned long long)D, (unsigned long long)M, (unsigned long long)c,
                 (unsigned long long)c * D, TC_KMAJOR, 0, 1};
       if ((rc = tc_gemm(A, Bm, B, D, c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
+      tm.mark("dP tc-gemm");
     }
-    return launch_rowdot(dP, P, (long long)B * M, D, delta, s);
+    rc = launch_rowdot(dP, P, (long long)B * M, D, delta, s);
+    tm.mark("rowdot");
+    return rc;
   }
   {  // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]
     GemmDesc g{};

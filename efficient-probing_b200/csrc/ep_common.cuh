@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdio>
 #include "../../include/ep_b200.h"
 
 // every kernel launch in the library is followed by this: error check + launch accounting
@@ -66,6 +67,27 @@ __device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
 }
 __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+extern int g_debug;
+// developer aid (ep_set_debug bit 5): CUDA-event time of every kernel of one call, printed to stderr
+struct StageTimer {
+  bool on; cudaStream_t s; cudaEvent_t ev[12]; const char* name[12]; int n = 0;
+  StageTimer(cudaStream_t st) : on((g_debug & 32) != 0), s(st) { if (on) mark("start"); }
+  void mark(const char* nm) {
+    if (!on || n >= 12) return;
+    cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], s); name[n++] = nm;
+  }
+  ~StageTimer() {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, "[ep timing] %-18s %8.1f us\n", name[i], ms * 1e3f);
+    }
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+  }
+};
+
+
 // ---- internal launchers shared between translation units (all return ep_status / cudaError) ----
 struct GemmDesc {      // C[z][i][j] = sum_k A[z][i][k] * B[z][k][j] (+ bias[z][j]); element strides
   const float* A; const float* B; float* C; const float* bias;
@@ -94,6 +116,7 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
 
 int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K, int Z, long long lda, long long ldb,
                    long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s);
+bool gemm_tn_ok(int I, int J, long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z);
 int launch_transpose_round(const float* src, float* dst, int R, int Cc, int Z, long long src_z, long long dst_z,
                            cudaStream_t s);
 

@@ -139,18 +139,32 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16);
     float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
     const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
+    const bool vec = g.c_col == 1 && (g.c_row % 4) == 0 && (g.c_z % 4) == 0 && (j0 % 4) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     for (int c0 = 0; c0 < g.NT; c0 += 16) {
       uint32_t r[16];
       tmem_ld16(acc + (uint32_t)c0, r);
       tmem_ld_wait();
       if (row < g.I) {
+        if (vec && j0 + c0 + 16 <= g.J) {                      // 64 contiguous bytes per lane
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = j0 + c0 + i;
-          if (col < g.J) {
-            float v = __uint_as_float(r[i]) + (bias ? __ldg(bias + col) : 0.f);
-            if (g.round_tf32) v = to_tf32(v);
-            crow[(long long)col * g.c_col] = v;
+          for (int i = 0; i < 16; ++i) {
+            v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + j0 + c0 + i) : 0.f);
+            if (g.round_tf32) v[i] = to_tf32(v[i]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(crow + j0 + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = j0 + c0 + i;
+            if (col < g.J) {
+              float v = __uint_as_float(r[i]) + (bias ? __ldg(bias + col) : 0.f);
+              if (g.round_tf32) v = to_tf32(v);
+              crow[(long long)col * g.c_col] = v;
+            }
           }
         }
       }

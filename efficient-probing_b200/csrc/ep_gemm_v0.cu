@@ -121,12 +121,18 @@ int launch_rowdot(const float* a, const float* b, long long rows, int cols, floa
 // ------------------------------------------------------------------------------------------------
 namespace ep {
 
-constexpr int TN_BI = 64, TN_BJ = 128, TN_BK = 16, TN_LDA = TN_BI + 8, TN_LDB = TN_BJ + 8;
+constexpr int TN_BI = 64, TN_BJ = 128, TN_BK = 16, TN_LDA = TN_BI + 8, TN_LDB = TN_BJ + 8, TN_STAGES = 4;
+constexpr int TN_STAGE_FLOATS = TN_BK * (TN_LDA + TN_LDB);
 
 __device__ __forceinline__ uint32_t f2tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return r;
+}
+// 16-byte async copy global -> shared; bytes beyond src_bytes are zero-filled (src_bytes in {0, 16})
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
 
 struct GemmTN {
@@ -135,9 +141,9 @@ struct GemmTN {
   long long lda, ldb, ldc, a_z, b_z, c_z;
 };
 
+// requires I % 4 == 0, J % 4 == 0, lda/ldb/a_z/b_z % 4 == 0 and 16-byte aligned bases
 __global__ void __launch_bounds__(256) gemm_tn_mma_kernel(GemmTN g) {
-  __shared__ __align__(16) float As[2][TN_BK][TN_LDA];
-  __shared__ __align__(16) float Bs[2][TN_BK][TN_LDB];
+  extern __shared__ __align__(16) float tn_smem[];
   const int z = blockIdx.z;
   const float* A = g.A + (long long)z * g.a_z;
   const float* B = g.B + (long long)z * g.b_z;
@@ -148,52 +154,53 @@ __global__ void __launch_bounds__(256) gemm_tn_mma_kernel(GemmTN g) {
   const int gq = lane >> 2, tq = lane & 3;
   float acc[2][4][4] = {};
 
-  auto load_stage = [&](int st, int k0) {
-    // A chunk: 16 k x 64 i = 256 float4; B chunk: 16 k x 128 j = 512 float4
-    for (int e = threadIdx.x; e < 256; e += 256) {
-      const int k = e >> 4, i = (e & 15) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + k < g.K && i0 + i < g.I) {
-        const float* p = A + (long long)(k0 + k) * g.lda + i0 + i;
-        if (i0 + i + 3 < g.I) v = __ldg(reinterpret_cast<const float4*>(p));
-        else { v.x = __ldg(p); if (i0 + i + 1 < g.I) v.y = __ldg(p + 1); if (i0 + i + 2 < g.I) v.z = __ldg(p + 2); }
-      }
-      *reinterpret_cast<float4*>(&As[st][k][i]) = v;
+  auto issue_stage = [&](int st, int k0) {
+    float* As = tn_smem + st * TN_STAGE_FLOATS;
+    float* Bs = As + TN_BK * TN_LDA;
+    {  // A chunk: 16 k x 64 i = 256 float4, one per thread
+      const int k = threadIdx.x >> 4, i = (threadIdx.x & 15) * 4;
+      const bool ok = k0 + k < g.K && i0 + i < g.I;
+      cp_async16(As + k * TN_LDA + i, ok ? A + (long long)(k0 + k) * g.lda + i0 + i : A, ok ? 16 : 0);
     }
-    for (int e = threadIdx.x; e < 512; e += 256) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // B chunk: 16 k x 128 j = 512 float4, two per thread
+      const int e = threadIdx.x + 256 * h;
       const int k = e >> 5, j = (e & 31) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + k < g.K && j0 + j < g.J) {
-        const float* p = B + (long long)(k0 + k) * g.ldb + j0 + j;
-        if (j0 + j + 3 < g.J) v = __ldg(reinterpret_cast<const float4*>(p));
-        else { v.x = __ldg(p); if (j0 + j + 1 < g.J) v.y = __ldg(p + 1); if (j0 + j + 2 < g.J) v.z = __ldg(p + 2); }
-      }
-      *reinterpret_cast<float4*>(&Bs[st][k][j]) = v;
+      const bool ok = k0 + k < g.K && j0 + j < g.J;
+      cp_async16(Bs + k * TN_LDB + j, ok ? B + (long long)(k0 + k) * g.ldb + j0 + j : B, ok ? 16 : 0);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   const int nk = (g.K + TN_BK - 1) / TN_BK;
-  load_stage(0, 0);
-  __syncthreads();
+#pragma unroll
+  for (int st = 0; st < TN_STAGES - 1; ++st) {
+    if (st < nk) issue_stage(st, st * TN_BK);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int kc = 0; kc < nk; ++kc) {
-    const int st = kc & 1;
-    if (kc + 1 < nk) load_stage(st ^ 1, (kc + 1) * TN_BK);
+    asm volatile("cp.async.wait_group %0;" ::"n"(TN_STAGES - 2) : "memory");
+    __syncthreads();
+    if (kc + TN_STAGES - 1 < nk) issue_stage((kc + TN_STAGES - 1) % TN_STAGES, (kc + TN_STAGES - 1) * TN_BK);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* As = tn_smem + (kc % TN_STAGES) * TN_STAGE_FLOATS;
+    const float* Bs = As + TN_BK * TN_LDA;
 #pragma unroll
     for (int kk = 0; kk < TN_BK; kk += 8) {
       uint32_t a[2][4], b[4][2];
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         const int i = wi + mi * 16 + gq;
-        a[mi][0] = f2tf32(As[st][kk + tq][i]);
-        a[mi][1] = f2tf32(As[st][kk + tq][i + 8]);
-        a[mi][2] = f2tf32(As[st][kk + tq + 4][i]);
-        a[mi][3] = f2tf32(As[st][kk + tq + 4][i + 8]);
+        a[mi][0] = f2tf32(As[(kk + tq) * TN_LDA + i]);
+        a[mi][1] = f2tf32(As[(kk + tq) * TN_LDA + i + 8]);
+        a[mi][2] = f2tf32(As[(kk + tq + 4) * TN_LDA + i]);
+        a[mi][3] = f2tf32(As[(kk + tq + 4) * TN_LDA + i + 8]);
       }
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const int j = wj + ni * 8 + gq;
-        b[ni][0] = f2tf32(Bs[st][kk + tq][j]);
-        b[ni][1] = f2tf32(Bs[st][kk + tq + 4][j]);
+        b[ni][0] = f2tf32(Bs[(kk + tq) * TN_LDB + j]);
+        b[ni][1] = f2tf32(Bs[(kk + tq + 4) * TN_LDB + j]);
       }
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
@@ -204,7 +211,6 @@ __global__ void __launch_bounds__(256) gemm_tn_mma_kernel(GemmTN g) {
               : "+f"(acc[mi][ni][0]), "+f"(acc[mi][ni][1]), "+f"(acc[mi][ni][2]), "+f"(acc[mi][ni][3])
               : "r"(a[mi][0]), "r"(a[mi][1]), "r"(a[mi][2]), "r"(a[mi][3]), "r"(b[ni][0]), "r"(b[ni][1]));
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
@@ -214,20 +220,28 @@ __global__ void __launch_bounds__(256) gemm_tn_mma_kernel(GemmTN g) {
       for (int h = 0; h < 2; ++h) {
         const int i = i0 + wi + mi * 16 + gq + h * 8;
         const int j = j0 + wj + ni * 8 + tq * 2;
-        if (i < g.I) {
-          if (j < g.J) C[(long long)i * g.ldc + j] = acc[mi][ni][2 * h];
-          if (j + 1 < g.J) C[(long long)i * g.ldc + j + 1] = acc[mi][ni][2 * h + 1];
-        }
+        if (i < g.I && j < g.J)                                 // J even: j and j + 1 are both in range
+          *reinterpret_cast<float2*>(C + (long long)i * g.ldc + j) = make_float2(acc[mi][ni][2 * h], acc[mi][ni][2 * h + 1]);
       }
+}
+
+bool gemm_tn_ok(int I, int J, long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z) {
+  return I % 4 == 0 && J % 4 == 0 && ((lda | ldb | a_z | b_z) & 3) == 0 && ((ldc | c_z) & 1) == 0;
 }
 
 int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K, int Z, long long lda, long long ldb,
                    long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s) {
   if (I <= 0 || J <= 0 || K <= 0 || Z <= 0) return EP_ERR_SHAPE;
-  if ((lda | ldb | a_z | b_z) & 3) return EP_ERR_ALIGN;
+  if (!gemm_tn_ok(I, J, lda, ldb, ldc, a_z, b_z, c_z)) return EP_ERR_ALIGN;
   GemmTN g{A, B, C, I, J, K, lda, ldb, ldc, a_z, b_z, c_z};
+  const int smem = TN_STAGES * TN_STAGE_FLOATS * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    EP_CUDA(cudaFuncSetAttribute(gemm_tn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
   dim3 grid((J + TN_BJ - 1) / TN_BJ, (I + TN_BI - 1) / TN_BI, Z);
-  gemm_tn_mma_kernel<<<grid, 256, 0, s>>>(g);
+  gemm_tn_mma_kernel<<<grid, 256, smem, s>>>(g);
   EP_LAUNCH_CHECK();
   return 0;
 }

@@ -461,25 +461,6 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int npart
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// developer aid (ep_set_debug bit 5): CUDA-event time of every kernel of one call, printed to stderr
-struct StageTimer {
-  bool on; cudaStream_t s; cudaEvent_t ev[12]; const char* name[12]; int n = 0;
-  StageTimer(cudaStream_t st) : on((g_debug & 32) != 0), s(st) { if (on) mark("start"); }
-  void mark(const char* nm) {
-    if (!on || n >= 12) return;
-    cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], s); name[n++] = nm;
-  }
-  ~StageTimer() {
-    if (!on) return;
-    cudaStreamSynchronize(s);
-    for (int i = 1; i < n; ++i) {
-      float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      fprintf(stderr, "[ep timing] %-18s %8.1f us\n", name[i], ms * 1e3f);
-    }
-    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
-  }
-};
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

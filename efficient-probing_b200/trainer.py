@@ -278,7 +278,11 @@ class EPHeadTrainer:
         """model.eval() forward (BatchNorm on running statistics), engine_finetune.py:106-166."""
         self._cx = self.x
         self.x.copy_(x, non_blocking=True)
-        self._forward(training=False)
+        self.lib.ep_set_gemm_mode(1)          # evaluation: fp32 contractions, predictions must not move
+        try:
+            self._forward(training=False)
+        finally:
+            self.lib.ep_set_gemm_mode(0)
         return self.logits.clone()
 
     def mean_loss(self) -> float:

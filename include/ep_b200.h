@@ -48,6 +48,10 @@ int ep_device_check(void);
 /* Select the pooling kernel family: 0 = automatic (tcgen05 kernels where the shape allows, else the
  * general kernels), 1 = force the general CUDA-core kernels, 2 = force tcgen05 (error if unsupported). */
 int ep_set_kernel_mode(int mode);
+/* Precision of the head's small dense contractions (value projection, classifier and their gradients):
+ * 0 (default) = TF32 tensor cores, operands rounded to nearest tf32, fp32 accumulate (~3e-4 relative);
+ * 1 = fp32 FMA on the CUDA cores (evaluation, where top-1 decisions must not move). */
+int ep_set_gemm_mode(int mode);
 /* Which family the last ep_fwd/ep_bwd call on this thread used (1 = general, 2 = tcgen05). */
 int ep_last_kernel_family(void);
 /* Developer knob for performance experiments (results are WRONG when non-zero); 0 in normal use. */
