@@ -65,9 +65,9 @@ int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
-  w.w_r = off;   off += align_up((size_t)D * D * sizeof(float), 256);       // >= (D/d_out) * D
-  w.w_t = off;   off += align_up((size_t)D * D * sizeof(float), 256);       // per-query transposed copy
-  w.g_r = off;   off += align_up((size_t)B * D * sizeof(float), 256);       // >= B * D/d_out
+  w.w_r = off;   off += 0;                                                   // (unused)
+  w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
+  w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
   w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
   w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
@@ -108,26 +108,23 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   const Ws w = carve(B, N, D, M);
   if (w.total > 0 && (!workspace || workspace_bytes < w.total)) return EP_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
+  // P stays exact fp32: it is also the saved tensor behind delta = dP . P in the backward pass, and the TF32
+  // GEMM that consumes it tolerates the hardware's truncation of this one operand (the weight side is rounded)
+  const int round_p = 0;
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
-    rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, (char*)workspace + w.sm100, s);
+    rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p,
+                        (char*)workspace + w.sm100, s);
   } else {
     if (rc) return rc;
     t_last_family = 1;
-    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, s);
+    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p, s);
   }
   if (rc) return rc;
   // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
   const int Dp = D / d_out, c = Dp / M;
-  if (use_tc() && c % 4 == 0) {
-    float* w_r = (float*)((char*)workspace + w.w_r);
-    if ((rc = launch_round_tf32(v_w, w_r, (size_t)Dp * D, s))) return rc;
-    TcSide A{P, (unsigned long long)D, (unsigned long long)M, (unsigned long long)B, (unsigned long long)D,
-             (unsigned long long)M * D, TC_KMAJOR, 1, 1};
-    TcSide Bm{w_r, (unsigned long long)D, (unsigned long long)c, (unsigned long long)M, (unsigned long long)D,
-              (unsigned long long)c * D, TC_KMAJOR, 0, 1};
-    return tc_gemm(A, Bm, B, c, D, M, round_nt(c), out, Dp, 1, c, v_b, c, 0, s);
-  }
+  if (use_tc() && D % 4 == 0)       // P is too large to copy: 3xTF32 in registers (mma.sync), P read once
+    return launch_gemm_nt3(P, v_w, out, v_b, B, c, D, M, (long long)M * D, D, Dp, D, (long long)c * D, c, c, s);
   GemmDesc g{};
   g.A = P; g.B = v_w; g.C = out; g.bias = v_b;
   g.I = B; g.J = c; g.K = D; g.Z = M;
@@ -151,23 +148,21 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
   int rc;
   StageTimer tm(s);
   if (use_tc() && c % 4 == 0) {
-    float* g_r = (float*)((char*)workspace + w.g_r);
-    if ((rc = launch_round_tf32(g_out, g_r, (size_t)B * Dp, s))) return rc;
-    tm.mark("round g");
     // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch, both operands
     // batch-major -> TF32 mma.sync "TN" kernel reading them as they lie
     if ((rc = launch_gemm_tn(g_out, P, d_v_w, c, D, B, M, Dp, (long long)M * D, D, c, D, (long long)c * D, s))) return rc;
     tm.mark("dW tn-gemm");
     if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
-    {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05 with a per-query transposed weight copy
-      float* w_t = (float*)((char*)workspace + w.w_t);            // w_t[m][d][j] = tf32(v_w[m*c + j][d])
-      if ((rc = launch_transpose_round(v_w, w_t, c, D, M, (long long)c * D, (long long)c * D, s))) return rc;
-      tm.mark("transpose W");
-      TcSide A{g_r, (unsigned long long)c, (unsigned long long)M, (unsigned long long)B, (unsigned long long)c,
-               (unsigned long long)Dp, TC_KMAJOR, 1, 1};
-      TcSide Bm{w_t, (unsigned long long)c, (unsigned long long)D, (unsigned long long)M, (unsigned long long)c,
-                (unsigned long long)c * D, TC_KMAJOR, 0, 1};
-      if ((rc = tc_gemm(A, Bm, B, D, c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
+    {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05, 3xTF32 (dP drives the query gradient)
+      float* g3 = (float*)((char*)workspace + w.g_r);              // [(b, m)][3c]  = [big | small | big]
+      float* w3 = (float*)((char*)workspace + w.w_t);              // [m][d][3c]    = [big | big | small]
+      if ((rc = launch_split3(g_out, g3, (long long)B * M, c, c, 0, s))) return rc;
+      if ((rc = launch_split3_transpose(v_w, w3, c, D, M, (long long)c * D, (long long)3 * c * D, 1, s))) return rc;
+      tm.mark("split3 g, W");
+      const unsigned long long c3 = 3ull * c;
+      TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1};
+      TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1};
+      if ((rc = tc_gemm(A, Bm, B, D, 3 * c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
       tm.mark("dP tc-gemm");
     }
     rc = launch_rowdot(dP, P, (long long)B * M, D, delta, s);
@@ -242,22 +237,23 @@ extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_to
   float* rowmax = (float*)workspace;
   float* rowsum = rowmax + (size_t)B * M;
   t_last_family = 1;
-  return pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, nullptr, nullptr, rowmax, rowsum, attn,
+  return pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, nullptr, nullptr, rowmax, rowsum, attn, 0,
                      (cudaStream_t)stream);
 }
 
 extern "C" size_t ep_linear_workspace_bytes(int B, int F, int K) {
   if (B <= 0 || F <= 0 || K <= 0) return 0;
-  return 2 * align_up((size_t)K * F * 4, 256) + align_up((size_t)B * F * 4, 256) + align_up((size_t)B * K * 4, 256);
+  return 2 * align_up((size_t)3 * K * F * 4, 256) + align_up((size_t)3 * B * F * 4, 256) +
+         align_up((size_t)3 * B * K * 4, 256);
 }
 namespace {
 struct LinWs { float *w_r, *w_t, *y_r, *d_r; };
 bool lin_ws(void* ws, size_t bytes, int B, int F, int K, LinWs* o) {
   if (!ws || bytes < ep_linear_workspace_bytes(B, F, K)) return false;
   char* p = (char*)ws;
-  o->w_r = (float*)p; p += align_up((size_t)K * F * 4, 256);
-  o->w_t = (float*)p; p += align_up((size_t)K * F * 4, 256);
-  o->y_r = (float*)p; p += align_up((size_t)B * F * 4, 256);
+  o->w_r = (float*)p; p += align_up((size_t)3 * K * F * 4, 256);
+  o->w_t = (float*)p; p += align_up((size_t)3 * K * F * 4, 256);
+  o->y_r = (float*)p; p += align_up((size_t)3 * B * F * 4, 256);
   o->d_r = (float*)p;
   return true;
 }
@@ -270,14 +266,13 @@ extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int
   cudaStream_t s = (cudaStream_t)stream;
   LinWs lw;
   if (use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw)) {
-    int rc;
-    if ((rc = launch_round_tf32(W, lw.w_r, (size_t)K * F, s))) return rc;
-    if ((rc = launch_round_tf32(y, lw.y_r, (size_t)B * F, s))) return rc;
-    TcSide A{lw.y_r, (unsigned long long)F, (unsigned long long)B, 1ull, (unsigned long long)F,
-             (unsigned long long)B * F, TC_KMAJOR, 0, 1};
-    TcSide Bm{lw.w_r, (unsigned long long)F, (unsigned long long)K, 1ull, (unsigned long long)F,
-              (unsigned long long)K * F, TC_KMAJOR, 0, 1};
-    return tc_gemm(A, Bm, B, K, F, 1, 128, logits, K, 1, 0, b, 0, 0, s);
+    int rc;                                                     // 3xTF32: y' = [big|small|big], W' = [big|big|small]
+    if ((rc = launch_split3(W, lw.w_r, K, F, F, 1, s))) return rc;
+    if ((rc = launch_split3(y, lw.y_r, B, F, F, 0, s))) return rc;
+    const unsigned long long F3 = 3ull * F;
+    TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1};
+    TcSide Bm{lw.w_r, F3, (unsigned long long)K, 1ull, F3, F3 * K, TC_KMAJOR, 0, 1};
+    return tc_gemm(A, Bm, B, K, 3 * F, 1, 128, logits, K, 1, 0, b, 0, 0, s);
   }
   GemmDesc g{};
   g.A = y; g.B = W; g.C = logits; g.bias = b;
@@ -294,7 +289,7 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   int rc;
   LinWs lw;
   const bool tc = use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw);
-  if (tc && (rc = launch_round_tf32(dlogits, lw.d_r, (size_t)B * K, s))) return rc;
+  (void)0;
   if (dW) {
     if (!y) return EP_ERR_NULL;
     if (tc) {                      // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: batch-major operands, "TN" kernel
@@ -310,13 +305,13 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   if (db && (rc = launch_colsum(dlogits, B, K, db, s))) return rc;
   if (dy) {
     if (!W) return EP_ERR_NULL;
-    if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05 with a transposed weight copy
-      if ((rc = launch_transpose_round(W, lw.w_t, K, F, 1, 0, 0, s))) return rc;     // w_t[f][k]
-      TcSide A{lw.d_r, (unsigned long long)K, (unsigned long long)B, 1ull, (unsigned long long)K,
-               (unsigned long long)B * K, TC_KMAJOR, 0, 1};
-      TcSide Bm{lw.w_t, (unsigned long long)K, (unsigned long long)F, 1ull, (unsigned long long)K,
-                (unsigned long long)K * F, TC_KMAJOR, 0, 1};
-      if ((rc = tc_gemm(A, Bm, B, F, K, 1, 128, dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
+    if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05, 3xTF32, transposed weight copy
+      if ((rc = launch_split3(dlogits, lw.d_r, B, K, K, 0, s))) return rc;            // [b][3K]
+      if ((rc = launch_split3_transpose(W, lw.w_t, K, F, 1, 0, 0, 1, s))) return rc;  // [f][3K]
+      const unsigned long long K3 = 3ull * K;
+      TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1};
+      TcSide Bm{lw.w_t, K3, (unsigned long long)F, 1ull, K3, K3 * F, TC_KMAJOR, 0, 1};
+      if ((rc = tc_gemm(A, Bm, B, F, 3 * K, 1, 128, dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
     } else {
       GemmDesc g{};
       g.A = dlogits; g.B = W; g.C = dy;

@@ -117,11 +117,15 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
 int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K, int Z, long long lda, long long ldb,
                    long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s);
 bool gemm_tn_ok(int I, int J, long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z);
-int launch_transpose_round(const float* src, float* dst, int R, int Cc, int Z, long long src_z, long long dst_z,
-                           cudaStream_t s);
+int launch_split3(const float* src, float* dst, long long R, int K, long long ld, int kind, cudaStream_t s);
+int launch_split3_transpose(const float* src, float* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
+                            cudaStream_t s);
+int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias, int I, int J, int K, int Z,
+                    long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z,
+                    long long bias_z, cudaStream_t s);
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
-                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, cudaStream_t s);
+                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s);
 int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 const float* rowmax, const float* rowsum, const float* dP, const float* delta,
                 float* dq_slots, int n_slots, float* d_cls, cudaStream_t s);

@@ -3,6 +3,8 @@
 // tensor-core kernels replace it where the layout allows.
 #include "ep_common.cuh"
 
+#include <algorithm>
+
 namespace ep {
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -246,26 +248,178 @@ int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K
   return 0;
 }
 
-// dst[z][c][r] = tf32(src[z][r][c]): K-major (transposed) copy of a weight block for the tcgen05 GEMMs
-__global__ void transpose_round_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc,
-                                       long long src_z, long long dst_z) {
+// ------------------------------------------------------------------------------------------------
+// 3xTF32 operand preparation for the tcgen05 GEMMs.  x = big + small with big = tf32(x), small =
+// tf32(x - big); A.B ~= A_big.B_big + A_small.B_big + A_big.B_small is evaluated as ONE TF32 GEMM over
+// a contraction three times as long:  A' = [big | small | big],  B' = [big | big | small]  (along K).
+// Both operands are small (weights, (B, D') activations), so the copies cost a few microseconds and
+// the product is accurate to ~1e-6 instead of TF32's 3e-4.
+//   kind 0: A-type, kind 1: B-type.  transpose: dst rows are src columns (weights read MN-major).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3_store(float* drow, int K, int k, float x, int kind) {
+  const float big = round_tf32(x);
+  const float small = round_tf32(x - big);
+  drow[k] = big;
+  drow[K + k] = kind == 0 ? small : big;
+  drow[2 * K + k] = kind == 0 ? big : small;
+}
+
+// src [R x K] (row stride ld) -> dst [R x 3K]
+__global__ void split3_kernel(const float* __restrict__ src, float* __restrict__ dst, long long R, int K, long long ld,
+                              int kind) {
+  const long long total = R * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K;
+    const int k = (int)(i - r * K);
+    split3_store(dst + r * 3 * K, K, k, __ldg(src + r * ld + k), kind);
+  }
+}
+int launch_split3(const float* src, float* dst, long long R, int K, long long ld, int kind, cudaStream_t s) {
+  const long long total = R * K;
+  split3_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 8 * kNumSMs), 256, 0, s>>>(src, dst, R, K, ld, kind);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+// src[z] is [K x R] (K rows, row stride R); dst[z] is [R x 3K]  (the transposed, K-major copy)
+__global__ void split3_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int R,
+                                        long long src_z, long long dst_z, int kind) {
   __shared__ float tile[32][33];
-  const float* s = src + (long long)blockIdx.z * src_z;
-  float* d = dst + (long long)blockIdx.z * dst_z;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const float* sp = src + (long long)blockIdx.z * src_z;
+  float* dp = dst + (long long)blockIdx.z * dst_z;
+  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < Cc) ? s[(long long)r * Cc + c] : 0.f;
+    const int k = k0 + i, r = r0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && r < R) ? sp[(long long)k * R + r] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < R && c < Cc) d[(long long)c * R + r] = round_tf32(tile[threadIdx.x][i]);
+    const int r = r0 + i, k = k0 + threadIdx.x;
+    if (r < R && k < K) split3_store(dp + (long long)r * 3 * K, K, k, tile[threadIdx.x][i], kind);
   }
 }
-int launch_transpose_round(const float* src, float* dst, int R, int Cc, int Z, long long src_z, long long dst_z,
-                           cudaStream_t s) {
-  transpose_round_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32, Z), dim3(32, 8), 0, s>>>(src, dst, R, Cc, src_z, dst_z);
+int launch_split3_transpose(const float* src, float* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
+                            cudaStream_t s) {
+  split3_transpose_kernel<<<dim3((R + 31) / 32, (K + 31) / 32, Z), dim3(32, 8), 0, s>>>(src, dst, K, R, src_z, dst_z, kind);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C[z][i][j] = sum_k A[z][i][k] * B[z][j][k] (+ bias[z][j])  ("NT", both K-contiguous) with 3xTF32 done
+// in registers: for the one product whose A operand (the pooled tokens P, B*M*D floats) is too large
+// to copy.  mma.sync m16n8k8, cp.async pipeline, 64 x 32 tile (the per-query projection is 32 wide).
+// ------------------------------------------------------------------------------------------------
+constexpr int NT_BI = 64, NT_BJ = 32, NT_BK = 32, NT_LD = NT_BK + 4, NT_STAGES = 4;
+constexpr int NT_STAGE_FLOATS = (NT_BI + NT_BJ) * NT_LD;
+
+struct GemmNT {
+  const float* A; const float* B; float* C; const float* bias;
+  int I, J, K;
+  long long lda, ldb, ldc, a_z, b_z, c_z, bias_z;
+};
+
+__global__ void __launch_bounds__(128) gemm_nt_3xtf32_kernel(GemmNT g) {
+  extern __shared__ __align__(16) float nt_smem[];
+  const int z = blockIdx.z;
+  const float* A = g.A + (long long)z * g.a_z;
+  const float* B = g.B + (long long)z * g.b_z;
+  float* C = g.C + (long long)z * g.c_z;
+  const int i0 = blockIdx.y * NT_BI, j0 = blockIdx.x * NT_BJ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wi = warp * 16;                                    // 4 warps x 16 rows, all 32 columns
+  const int gq = lane >> 2, tq = lane & 3;
+  float acc[4][4] = {};
+
+  auto issue_stage = [&](int st, int k0) {
+    float* As = nt_smem + st * NT_STAGE_FLOATS;
+    float* Bs = As + NT_BI * NT_LD;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {                              // A: 64 rows x 32 k = 512 float4
+      const int e = threadIdx.x + 128 * h;
+      const int i = e >> 3, k = (e & 7) * 4;
+      const bool ok = i0 + i < g.I && k0 + k < g.K;
+      cp_async16(As + i * NT_LD + k, ok ? A + (long long)(i0 + i) * g.lda + k0 + k : A, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                              // B: 32 rows x 32 k = 256 float4
+      const int e = threadIdx.x + 128 * h;
+      const int j = e >> 3, k = (e & 7) * 4;
+      const bool ok = j0 + j < g.J && k0 + k < g.K;
+      cp_async16(Bs + j * NT_LD + k, ok ? B + (long long)(j0 + j) * g.ldb + k0 + k : B, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nk = (g.K + NT_BK - 1) / NT_BK;
+#pragma unroll
+  for (int st = 0; st < NT_STAGES - 1; ++st) {
+    if (st < nk) issue_stage(st, st * NT_BK);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kc = 0; kc < nk; ++kc) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NT_STAGES - 2) : "memory");
+    __syncthreads();
+    if (kc + NT_STAGES - 1 < nk) issue_stage((kc + NT_STAGES - 1) % NT_STAGES, (kc + NT_STAGES - 1) * NT_BK);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* As = nt_smem + (kc % NT_STAGES) * NT_STAGE_FLOATS;
+    const float* Bs = As + NT_BI * NT_LD;
+#pragma unroll
+    for (int kk = 0; kk < NT_BK; kk += 8) {
+      float af[4], bf[4][2];
+      af[0] = As[(wi + gq) * NT_LD + kk + tq];
+      af[1] = As[(wi + gq + 8) * NT_LD + kk + tq];
+      af[2] = As[(wi + gq) * NT_LD + kk + tq + 4];
+      af[3] = As[(wi + gq + 8) * NT_LD + kk + tq + 4];
+      uint32_t ab[4], as_[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ab[e] = f2tf32(af[e]); as_[e] = f2tf32(af[e] - __uint_as_float(ab[e])); }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        bf[ni][0] = Bs[(ni * 8 + gq) * NT_LD + kk + tq];
+        bf[ni][1] = Bs[(ni * 8 + gq) * NT_LD + kk + tq + 4];
+        uint32_t bb[2], bs[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { bb[e] = f2tf32(bf[ni][e]); bs[e] = f2tf32(bf[ni][e] - __uint_as_float(bb[e])); }
+#define EP_MMA_TF32(ACC, AA, BB)                                                                                   \
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+               : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                             \
+               : "r"(AA[0]), "r"(AA[1]), "r"(AA[2]), "r"(AA[3]), "r"(BB[0]), "r"(BB[1]))
+        EP_MMA_TF32(acc[ni], as_, bb);
+        EP_MMA_TF32(acc[ni], ab, bs);
+        EP_MMA_TF32(acc[ni], ab, bb);
+#undef EP_MMA_TF32
+      }
+    }
+  }
+  const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + wi + gq + h * 8;
+      const int j = j0 + ni * 8 + tq * 2;
+      if (i < g.I) {
+        if (j < g.J) C[(long long)i * g.ldc + j] = acc[ni][2 * h] + (bias ? bias[j] : 0.f);
+        if (j + 1 < g.J) C[(long long)i * g.ldc + j + 1] = acc[ni][2 * h + 1] + (bias ? bias[j + 1] : 0.f);
+      }
+    }
+}
+
+int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias, int I, int J, int K, int Z,
+                    long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z,
+                    long long bias_z, cudaStream_t s) {
+  if (I <= 0 || J <= 0 || K <= 0 || Z <= 0) return EP_ERR_SHAPE;
+  if (((lda | ldb | a_z | b_z) & 3) || (K & 3)) return EP_ERR_ALIGN;
+  GemmNT g{A, B, C, bias, I, J, K, lda, ldb, ldc, a_z, b_z, c_z, bias_z};
+  const int smem = NT_STAGES * NT_STAGE_FLOATS * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    EP_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dim3 grid((J + NT_BJ - 1) / NT_BJ, (I + NT_BI - 1) / NT_BI, Z);
+  gemm_nt_3xtf32_kernel<<<grid, 128, smem, s>>>(g);
   EP_LAUNCH_CHECK();
   return 0;
 }

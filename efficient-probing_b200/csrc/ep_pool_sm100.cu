@@ -47,7 +47,7 @@ struct KSParams {
 };
 
 struct KPParams {
-  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, debug;
+  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, debug, round_out;
   const float* src;      // (B, M, N): logits (mode 0) or dS (mode 1)
   const float* rmax;     // mode 0
   const float* rsum;     // mode 0
@@ -370,7 +370,8 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
             if (m < p.M) {
               float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
               if (kMode == 0) {
-                v = round_tf32(v * __shfl_sync(0xffffffffu, invl[m >> 5], m & 31));   // P feeds TF32 GEMMs
+                v *= __shfl_sync(0xffffffffu, invl[m >> 5], m & 31);
+                if (p.round_out) v = round_tf32(v);          // P feeds the TF32 GEMMs: store it pre-rounded
                 if (!(p.debug & 2)) p.out[((size_t)b * p.M + m) * p.D + d] = v;
               } else {
                 p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
@@ -572,7 +573,7 @@ int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, 
 
 template <int kMode>
 int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const float* src, const float* rmax,
-              const float* rsum, float* out, int* groups_out, cudaStream_t s) {
+              const float* rsum, float* out, int* groups_out, int round_out, cudaStream_t s) {
   CUtensorMap tm_x;
   int rc;
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTokBlock))) return rc;
@@ -587,6 +588,7 @@ int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const f
   p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
   p.src = src; p.rmax = rmax; p.rsum = rsum; p.out = out;
   p.debug = g_debug;
+  p.round_out = round_out;
   if ((rc = set_dyn_smem(kp_kernel<kMode>, pl.kp_smem))) return rc;
   const int gx = std::max(1, std::min(B, kNumSMs / ysplit));
   if (groups_out) *groups_out = gx;
@@ -609,7 +611,7 @@ size_t sm100_workspace_bytes(int B, int N, int D, int M) {
 }
 
 int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, int D, int M, float* P, float* S,
-                   float* rowmax, float* rowsum, float* attn, void* ws, cudaStream_t s) {
+                   float* rowmax, float* rowsum, float* attn, int round_p, void* ws, cudaStream_t s) {
   const Plan pl = make_plan(N, D, M);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   const Ws100 w = carve100(B, N, D, M, pl);
@@ -626,7 +628,7 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   EP_LAUNCH_CHECK();
   tm.mark("rowstats");
   if (P == nullptr) return 0;
-  rc = launch_kp<0>(x, B, N, D, M, pl, S, rowmax, rowsum, P, nullptr, s);
+  rc = launch_kp<0>(x, B, N, D, M, pl, S, rowmax, rowsum, P, nullptr, round_p, s);
   tm.mark("kp<0> pool");
   return rc;
 }
@@ -647,7 +649,7 @@ int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int
   if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, dS, S, rowmax, rowsum, delta, s))) return rc;
   tm.mark("ks<1> dS");
   int groups = 0;
-  if ((rc = launch_kp<1>(x, B, N, D, M, pl, dS, nullptr, nullptr, part, &groups, s))) return rc;
+  if ((rc = launch_kp<1>(x, B, N, D, M, pl, dS, nullptr, nullptr, part, &groups, 0, s))) return rc;
   tm.mark("kp<1> dq");
   const size_t n = (size_t)M * D;
   reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, groups, n, scale, d_cls);

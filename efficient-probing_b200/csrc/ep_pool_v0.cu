@@ -95,7 +95,7 @@ template <typename XT>
 __global__ void __launch_bounds__(kThreads)
 pool_fwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, float scale, int N, int D, int M,
                    float* __restrict__ P, float* __restrict__ S_out, float* __restrict__ rowmax,
-                   float* __restrict__ rowsum, float* __restrict__ attn) {
+                   float* __restrict__ rowsum, float* __restrict__ attn, int round_p) {
   extern __shared__ __align__(16) float S[];
   const int b = blockIdx.x, LD = s_ld(M);
   const XT* xb = x + (size_t)b * N * D;
@@ -134,7 +134,8 @@ pool_fwd_v0_kernel(const XT* __restrict__ x, const float* __restrict__ cls, floa
       for (int j = 0; j < 32; ++j)
         if (mb + j < M)
           *reinterpret_cast<float2*>(P + ((size_t)b * M + mb + j) * D + dd) =
-              make_float2(round_tf32(acc[j][0]), round_tf32(acc[j][1]));          // P feeds TF32 GEMMs
+              round_p ? make_float2(round_tf32(acc[j][0]), round_tf32(acc[j][1]))   // P feeds TF32 GEMMs
+                      : make_float2(acc[j][0], acc[j][1]);
     }
   }
 }
@@ -185,17 +186,18 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
-                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, cudaStream_t s) {
+                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s) {
   if (M > 64) return EP_ERR_UNSUPPORTED;
   const size_t smem = pool_v0_smem_bytes(N, M);
   int rc;
   if (x_dtype == EP_DTYPE_BF16) {
     if ((rc = set_smem(pool_fwd_v0_kernel<__nv_bfloat16>, smem))) return rc;
     pool_fwd_v0_kernel<__nv_bfloat16><<<B, kThreads, smem, s>>>((const __nv_bfloat16*)x, cls, scale, N, D, M, P,
-                                                                 S_out, rowmax, rowsum, attn);
+                                                                 S_out, rowmax, rowsum, attn, round_p);
   } else {
     if ((rc = set_smem(pool_fwd_v0_kernel<float>, smem))) return rc;
-    pool_fwd_v0_kernel<float><<<B, kThreads, smem, s>>>((const float*)x, cls, scale, N, D, M, P, S_out, rowmax, rowsum, attn);
+    pool_fwd_v0_kernel<float><<<B, kThreads, smem, s>>>((const float*)x, cls, scale, N, D, M, P, S_out, rowmax, rowsum, attn,
+                                                        round_p);
   }
   EP_LAUNCH_CHECK();
   return 0;

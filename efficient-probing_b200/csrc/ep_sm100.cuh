@@ -6,7 +6,7 @@ namespace ep {
 bool sm100_supported(int x_dtype, int B, int N, int D, int M);
 size_t sm100_workspace_bytes(int B, int N, int D, int M);
 int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, int D, int M, float* P, float* S,
-                   float* rowmax, float* rowsum, float* attn, void* ws, cudaStream_t s);
+                   float* rowmax, float* rowsum, float* attn, int round_p, void* ws, cudaStream_t s);
 int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int D, int M, const float* rowmax,
                    const float* rowsum, const float* dP, const float* delta, float* d_cls, void* ws, cudaStream_t s);
 }  // namespace ep

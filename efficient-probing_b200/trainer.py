@@ -68,11 +68,14 @@ class EPHeadTrainer:
         self.trust = [p.ndim > 1 for p in self.params]                                   # util/lars.py:21
         # flat gradient buffer: large, early-ready tensors first, cls_token last
         sizes = {"fc_w": K * Dp, "fc_b": K, "v_w": Dp * D, "v_b": Dp if pool.v.bias is not None else 0, "cls": M * D}
-        self.flat_grad = torch.zeros(sum(sizes.values()), **f32)
+        # every slice starts on a 256-byte boundary (vector stores / TMA in the kernels); the padding is zero
+        pad = lambda n: (n + 63) // 64 * 64
+        self.flat_grad = torch.zeros(sum(pad(n) for n in sizes.values()), **f32)
         off, self.g = 0, {}
         for k, n in sizes.items():
             self.g[k] = self.flat_grad[off:off + n]
-            off += n
+            off += pad(n)
+        off -= pad(sizes["cls"]) - sizes["cls"]
         self.n_early = off - sizes["cls"]
         self.grads = [self.g["cls"], self.g["v_w"]] + ([self.g["v_b"]] if pool.v.bias is not None else []) + \
                      [self.g["fc_w"], self.g["fc_b"]]

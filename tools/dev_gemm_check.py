@@ -34,7 +34,7 @@ for (B, N, D, M, d_out) in [(256, 5, 256, 8, 1), (130, 3, 128, 32, 1), (64, 4, 2
     ref_dvw = torch.einsum("bmj,bmc->mjc", g.double().reshape(B, M, c), P.double()).reshape(Dp, D)
     # dP sits at the start of the pooling part of the workspace: find it via the known layout (w_r, g_r first)
     au = lambda v: (v + 255) // 256 * 256
-    off = 2 * au(D * D * 4) + au(B * D * 4)
+    off = au(3 * D * D * 4) + au(3 * B * D * 4)
     dP = ws[off: off + B * M * D * 4].view(torch.float32).reshape(B, M, D)
     ref_dP = torch.einsum("bmj,mjc->bmc", g.double().reshape(B, M, c), Wm)
     print((B, N, D, M, d_out), "out %.2e d_v_w %.2e dP %.2e" % (rel(out, ref_out), rel(dvw, ref_dvw), rel(dP, ref_dP)), flush=True)
