@@ -205,7 +205,7 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
   float* slots = (float*)((char*)workspace + w.slots);
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
-    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, dP, delta, d_cls_token,
+    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, dP, delta, 1, d_cls_token,
                           (char*)workspace + w.sm100, s);
   }
   if (rc) return rc;

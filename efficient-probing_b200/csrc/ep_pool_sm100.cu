@@ -9,14 +9,15 @@
 //               operand; the accumulators of ALL token tiles of a sample live in TMEM while the kernel
 //               walks d, so W is streamed once per sample and nothing large is resident.
 //   kp_kernel : the SAME 128-byte-swizzled x bytes are read as an MN-major A operand [128 d x 16 tokens]
-//               (instruction-descriptor transpose bit), V is written by a converter warpgroup as a
-//               K-major B operand [J x 64 tokens]; the (d x J) accumulators stay in TMEM per sample
-//               (forward) or for the whole launch (backward, gradients summed over the batch).
+//               (instruction-descriptor transpose bit); V arrives as operand-ready blocks [J x 64 tokens]
+//               (bf16 hi/lo rows, 128B-swizzle baked in) that the upstream kernel wrote to global memory,
+//               copied into the ring with one cp.async.bulk each; the (d x J) accumulators stay in TMEM
+//               per sample (forward) or for the whole launch (backward, gradients summed over the batch).
 // fp32 operands (queries, probabilities, gradients) enter as bf16 hi/lo pairs in adjacent operand
 // rows (j = 2m: hi, 2m+1: lo), so every product is exact and the sum carries ~16 mantissa bits; the
 // two accumulator columns are added when the result leaves TMEM.
 // Warp roles (one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (ks) / operand converter (kp), warps 8-11 = epilogue (kp).
+// allocator, warps 4-11 = epilogue (two warps per TMEM lane quadrant).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -38,27 +39,48 @@ constexpr int kBrickBytes = 2 * kTokBlock * 128;   // [64 tokens x 128 d] = two 
 constexpr int kSmemBudget = 220 * 1024;
 
 struct KSParams {
-  int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols;
-  float* out;            // (B, M, N)
+  int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols, nkb, ndelta;
+  float* out;            // mode 0: logits (B, M, N)
+  uint8_t* blocks;       // mode 1: dS as operand blocks [B][nkb][J rows x 64 tokens] bf16 hi/lo, swizzled
   const float* S;        // mode 1: saved logits
   const float* rmax;     // mode 1
   const float* rsum;     // mode 1
-  const float* delta;    // mode 1
+  const float* delta;    // mode 1: ndelta partial sums of delta, each (B, M)
 };
 
 struct KPParams {
   int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, debug, round_out;
-  const float* src;      // (B, M, N): logits (mode 0) or dS (mode 1)
-  const float* rmax;     // mode 0
+  const uint8_t* blocks; // operand blocks [B][nkb][J x 64 tokens]: exp(S - rowmax) (mode 0) or dS (mode 1)
   const float* rsum;     // mode 0
   float* out;            // mode 0: P (B, M, D); mode 1: partial dq (gridDim.x, M, D)
 };
+
+constexpr int kEpiWarps = 8;       // warps 4..11: two per TMEM lane quadrant
+constexpr int kThreads = 32 * (4 + kEpiWarps);
+
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (operand blocks are contiguous)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// byte offset of (operand row j, token t) inside a [J x 64 tokens] bf16 block (128-byte rows, 128B swizzle)
+__host__ __device__ __forceinline__ uint32_t block_offset(uint32_t j, uint32_t t) {
+  return j * 128u + (((t >> 3) ^ (j & 7u)) << 4) + (t & 7u) * 2u;
+}
+__device__ __forceinline__ void store_hilo(uint8_t* blk, int m, int t, float e) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(e);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
+  *reinterpret_cast<__nv_bfloat16*>(blk + block_offset(2 * m, t)) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(blk + block_offset(2 * m + 1, t)) = lo;
+}
 
 // ------------------------------------------------------------------------------------------------
 // logit-type kernel
 // ------------------------------------------------------------------------------------------------
 template <int kMode>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const KSParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -77,7 +99,7 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); }
@@ -139,15 +161,15 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp - 4;
+    // epilogue: warp (4 + 4h + q) reads TMEM lanes [32q, 32q+32) and takes every other (tile, 16-column)
+    // unit: units u = t * (J/16) + j0/16 with u % 2 == h
+    const int wq = (warp - 4) & 3, eh = (warp - 4) >> 2;
+    const int upt = p.J >> 4;
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       const int b = item / p.ngroups, g = item - b * p.ngroups;
       const int t0 = g * p.G, gt = min(p.G, p.ntiles - t0);
       const int buf = it % p.nbuf;
-      mbar_wait(tfull_bar(buf), ((uint32_t)(it / p.nbuf)) & 1u);
-      tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
       // mode 1: lane l keeps the row statistics of queries l and 32 + l of this sample
       float st_mx[2] = {0.f, 0.f}, st_inv[2] = {0.f, 0.f}, st_dl[2] = {0.f, 0.f};
       if (kMode == 1) {
@@ -158,40 +180,52 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             const size_t bm = (size_t)b * p.M + m;
             st_mx[h] = __ldg(p.rmax + bm);
             st_inv[h] = 1.f / __ldg(p.rsum + bm);
-            st_dl[h] = __ldg(p.delta + bm);
+            float dl = 0.f;
+            for (int q = 0; q < p.ndelta; ++q) dl += __ldg(p.delta + (size_t)q * p.B * p.M + bm);
+            st_dl[h] = dl;
           }
         }
       }
-      for (int t = 0; t < gt; ++t) {
+      mbar_wait(tfull_bar(buf), ((uint32_t)(it / p.nbuf)) & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
+      for (int u = eh; u < gt * upt; u += 2) {
+        const int t = u / upt, j0 = (u - t * upt) << 4;
         const int n = (t0 + t) * kTileRows + wq * 32 + lane;
-        for (int j0 = 0; j0 < p.J; j0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + (uint32_t)(t * p.J + j0), r);
-          // issue the global loads of this 8-query batch before the first use (they are independent;
-          // otherwise the load -> exp -> store chain serialises on memory latency)
-          float sv[8];
-          if (kMode == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = min((j0 >> 1) + i, p.M - 1);
-              sv[i] = (n < p.N) ? __ldg(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
-            }
-          }
-          tmem_ld_wait();
+        uint32_t r[16];
+        tmem_ld16(acc + (uint32_t)(t * p.J + j0), r);
+        // the global loads of this 8-query batch are issued before the first use (they are independent;
+        // otherwise the load -> exp -> store chain serialises on memory latency)
+        float sv[8];
+        if (kMode == 1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int m = (j0 >> 1) + i;                     // warp-uniform
+            const int m = min((j0 >> 1) + i, p.M - 1);
+            sv[i] = (n < p.N) ? __ldg(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
+          }
+        }
+        tmem_ld_wait();
+        uint8_t* blk = nullptr;
+        const int kb = n >> 6, tt = n & 63;
+        if (kMode == 1 && kb < p.nkb) blk = p.blocks + ((size_t)b * p.nkb + kb) * ((size_t)p.J * 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = (j0 >> 1) + i;                       // warp-uniform
+          float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
+          if (kMode == 0) {
+            if (m < p.M && n < p.N) p.out[((size_t)b * p.M + m) * p.N + n] = v;
+          } else {
+            // dS = A (dA - delta), written straight into the pool-type kernel's operand block; tokens
+            // past N and operand rows past 2M are written as zeros so the block needs no memset
+            float ds = 0.f;
             if (m < p.M) {
-              float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
-              if (kMode == 1) {
-                const int h = m >> 5, src = m & 31;
-                const float mx = __shfl_sync(0xffffffffu, st_mx[h], src);
-                const float inv = __shfl_sync(0xffffffffu, st_inv[h], src);
-                const float dl = __shfl_sync(0xffffffffu, st_dl[h], src);
-                v = __expf(sv[i] - mx) * inv * (v - dl);
-              }
-              if (n < p.N) p.out[((size_t)b * p.M + m) * p.N + n] = v;
+              const int h = m >> 5, src = m & 31;
+              const float mx = __shfl_sync(0xffffffffu, st_mx[h], src);
+              const float inv = __shfl_sync(0xffffffffu, st_inv[h], src);
+              const float dl = __shfl_sync(0xffffffffu, st_dl[h], src);
+              if (n < p.N) ds = __expf(sv[i] - mx) * inv * (v - dl);
             }
+            if (blk) store_hilo(blk, m, tt, ds);
           }
         }
       }
@@ -208,7 +242,7 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
 // pool-type kernel
 // ------------------------------------------------------------------------------------------------
 template <int kMode>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -228,14 +262,10 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.xslots; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
-    for (int s = 0; s < p.wslots; ++s) { mbar_init(wfull(s), 128); mbar_init(wempty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(afull(b), 1); mbar_init(aempty(b), 128); }
+    for (int s = 0; s < p.wslots; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(afull(b), 1); mbar_init(aempty(b), 32 * kEpiWarps); }
     fence_barrier_init();
   }
-  // operand rows that no query owns (2M..J-1) stay zero for the whole launch
-  for (uint32_t i = threadIdx.x; i < (uint32_t)p.wslots * wt_bytes / 16u; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem_gen + (wt_base - smem_base))[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
   if (warp == 0 && lane == 0) prefetch_tmap(&tm_x);
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -248,10 +278,15 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
   if (warp == 0) {
     if (lane == 0) {
       const uint64_t pol_x = policy_evict_first();
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, ws = 0;
+      uint32_t ph = 0, wph = 0;
       for (int b = blockIdx.x; b < p.B; b += gridDim.x)
-        for (int kb = 0; kb < p.nkb; ++kb)
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(wempty(ws), wph ^ 1u);                    // operand block of this token block
+          mbar_arrive_expect_tx(wfull(ws), wt_bytes);
+          bulk_load(wt_base + (uint32_t)ws * wt_bytes, p.blocks + ((size_t)b * p.nkb + kb) * wt_bytes, wt_bytes,
+                    wfull(ws));
+          if (++ws == p.wslots) { ws = 0; wph ^= 1u; }
           for (int sl = 0; sl < nsl; ++sl) {
             mbar_wait(xempty(s), ph ^ 1u);
             const uint32_t dst = smem_base + (uint32_t)s * kBrickBytes;
@@ -260,6 +295,7 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
             tma_load_3d_hint(dst + kBrickBytes / 2, &tm_x, xfull(s), d0 + sl * 128 + 64, kb * kTokBlock, b, pol_x);
             if (++s == p.xslots) { s = 0; ph ^= 1u; }
           }
+        }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -300,56 +336,10 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
       }
       if (kMode == 1) umma_commit(afull(0));
     }
-  } else if (warp >= 4 && warp < 8) {
-    // converter: fp32 (B, M, N) -> bf16 hi/lo K-major operand block [J rows x 64 tokens], 128B-swizzled.
-    // Thread (t, half) converts token t for queries m = half + 2u, eight at a time (loads first).
-    const int tid = threadIdx.x - 128;
-    const int t = tid & 63, half = tid >> 6;
-    const int nm = (p.M - half + 1) / 2;
-    int ws = 0;
-    uint32_t wph = 0;
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-      float mxl[2] = {0.f, 0.f};                             // lane l keeps rowmax of queries l and 32 + l
-      if (kMode == 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          mxl[h] = (h * 32 + lane < p.M) ? __ldg(p.rmax + (size_t)b * p.M + h * 32 + lane) : 0.f;
-      }
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int n = kb * kTokBlock + t;
-        const float* row = p.src + ((size_t)b * p.M + half) * p.N + n;
-        const uint32_t col = (uint32_t)(t & 7) * 2u;
-        uint8_t* wt = smem_gen + (wt_base - smem_base) + (size_t)ws * wt_bytes;
-        bool waited = false;
-        for (int u0 = 0; u0 < nm; u0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            v[u] = (n < p.N && u0 + u < nm && !(p.debug & 1)) ? __ldg(row + (size_t)(2 * (u0 + u)) * p.N) : 0.f;
-          if (!waited) { mbar_wait(wempty(ws), wph ^ 1u); waited = true; }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (u0 + u < nm && !(p.debug & 4)) {             // warp-uniform
-              const int m = half + 2 * (u0 + u);
-              float e = v[u];
-              if (kMode == 0) {
-                const float mx = __shfl_sync(0xffffffffu, mxl[m >> 5], m & 31);
-                e = (n < p.N) ? __expf(e - mx) : 0.f;
-              }
-              const __nv_bfloat16 hi = __float2bfloat16_rn(e);
-              const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
-              *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m, t >> 3) + col) = hi;
-              *reinterpret_cast<__nv_bfloat16*>(wt + sw128_offset(2 * m + 1, t >> 3) + col) = lo;
-            }
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(wfull(ws));
-        if (++ws == p.wslots) { ws = 0; wph ^= 1u; }
-      }
-    }
-  } else if (warp >= 8) {
-    const int wq = warp - 8;
+  } else if (warp >= 4) {
+    // epilogue: warp (4 + 4h + q) reads TMEM lanes [32q, 32q+32) and every other (slice, 16-column) unit
+    const int wq = (warp - 4) & 3, eh = (warp - 4) >> 2;
+    const int upt = p.J >> 4;
     auto drain = [&](int buf, int b) {
       const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
       float invl[2] = {1.f, 1.f};                            // lane l keeps 1/rowsum of queries l and 32 + l
@@ -358,24 +348,23 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
         for (int h = 0; h < 2; ++h)
           if (h * 32 + lane < p.M) invl[h] = 1.f / __ldg(p.rsum + (size_t)b * p.M + h * 32 + lane);
       }
-      for (int sl = 0; sl < ((p.debug & 8) ? 0 : nsl); ++sl) {
+      for (int u = eh; u < ((p.debug & 8) ? 0 : nsl * upt); u += 2) {
+        const int sl = u / upt, j0 = (u - sl * upt) << 4;
         const int d = d0 + sl * 128 + wq * 32 + lane;
-        for (int j0 = 0; j0 < p.J; j0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + (uint32_t)(sl * p.J + j0), r);
-          tmem_ld_wait();
+        uint32_t r[16];
+        tmem_ld16(acc + (uint32_t)(sl * p.J + j0), r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = (j0 >> 1) + i;                     // warp-uniform
-            if (m < p.M) {
-              float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
-              if (kMode == 0) {
-                v *= __shfl_sync(0xffffffffu, invl[m >> 5], m & 31);
-                if (p.round_out) v = round_tf32(v);          // P feeds the TF32 GEMMs: store it pre-rounded
-                if (!(p.debug & 2)) p.out[((size_t)b * p.M + m) * p.D + d] = v;
-              } else {
-                p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
-              }
+        for (int i = 0; i < 8; ++i) {
+          const int m = (j0 >> 1) + i;                       // warp-uniform
+          if (m < p.M) {
+            float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
+            if (kMode == 0) {
+              v *= __shfl_sync(0xffffffffu, invl[m >> 5], m & 31);
+              if (p.round_out) v = round_tf32(v);
+              if (!(p.debug & 2)) p.out[((size_t)b * p.M + m) * p.D + d] = v;
+            } else {
+              p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
             }
           }
         }
@@ -427,24 +416,36 @@ __global__ void split_hilo_kernel(const float* __restrict__ src, float scale, in
   }
 }
 
-// one warp per (b, m) row of the logits: rowmax, rowsum = sum exp(S - rowmax), optional attention map
-__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ S, long long rows, int N,
+// one warp per (b, j/2) operand row pair of the logits: rowmax, rowsum = sum exp(S - rowmax), optional
+// attention map, and (blocks != nullptr) exp(S - rowmax) as bf16 hi/lo operand blocks for the pool-type
+// kernel -- tokens past N and row pairs past M are written as zeros, so the blocks need no memset.
+__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ S, int B, int M, int J, int N, int nkb,
                                                        float* __restrict__ rmax, float* __restrict__ rsum,
-                                                       float* __restrict__ attn) {
+                                                       float* __restrict__ attn, uint8_t* __restrict__ blocks) {
+  const int pairs = J >> 1;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= rows) return;
+  if (r >= (long long)B * pairs) return;
+  const int b = (int)(r / pairs), m = (int)(r % pairs);
   const int lane = threadIdx.x & 31;
-  const float* row = S + r * N;
-  float mx = -INFINITY;
-  for (int n = lane; n < N; n += 32) mx = fmaxf(mx, row[n]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int n = lane; n < N; n += 32) sum += __expf(row[n] - mx);
-  sum = warp_sum(sum);
-  if (lane == 0) { rmax[r] = mx; rsum[r] = sum; }
-  if (attn) {
-    const float inv = 1.f / sum;
-    for (int n = lane; n < N; n += 32) attn[r * N + n] = __expf(row[n] - mx) * inv;
+  float mx = 0.f, inv = 0.f;
+  const float* row = S + ((size_t)b * M + min(m, M - 1)) * N;
+  if (m < M) {
+    mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, row[n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) sum += __expf(row[n] - mx);
+    sum = warp_sum(sum);
+    inv = 1.f / sum;
+    if (lane == 0) { rmax[(size_t)b * M + m] = mx; rsum[(size_t)b * M + m] = sum; }
+    if (attn)
+      for (int n = lane; n < N; n += 32) attn[((size_t)b * M + m) * N + n] = __expf(row[n] - mx) * inv;
+  }
+  if (blocks) {
+    for (int n = lane; n < nkb * kTokBlock; n += 32) {
+      const float e = (m < M && n < N) ? __expf(row[n] - mx) : 0.f;
+      store_hilo(blocks + ((size_t)b * nkb + (n >> 6)) * ((size_t)J * 128), m, n & 63, e);
+    }
   }
 }
 
@@ -537,9 +538,9 @@ struct Ws100 {
 Ws100 carve100(int B, int N, int D, int M, const Plan& pl) {
   Ws100 w;
   size_t off = 0;
-  w.qhl = off;  off += align_up((size_t)pl.J * D * 2, 256);
-  w.dphl = off; off += align_up((size_t)B * pl.J * D * 2, 256);
-  w.dS = off;   off += align_up((size_t)B * M * N * 4, 256);
+  w.qhl = off;  off += align_up((size_t)pl.J * D * 2, 1024);
+  w.dphl = off; off += align_up((size_t)B * pl.J * D * 2, 1024);
+  w.dS = off;   off += align_up((size_t)B * pl.nkb * pl.J * 128, 1024);   // operand blocks (exp(S - max) / dS)
   w.part = off; off += align_up((size_t)kNumSMs * M * D * 4, 256);
   w.S_unused = 0;
   w.total = off;
@@ -554,7 +555,8 @@ int set_dyn_smem(K kernel, size_t bytes) {
 
 template <int kMode>
 int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, int M, const Plan& pl, float* out,
-              const float* S, const float* rmax, const float* rsum, const float* delta, cudaStream_t s) {
+              uint8_t* blocks, const float* S, const float* rmax, const float* rsum, const float* delta, int ndelta,
+              cudaStream_t s) {
   CUtensorMap tm_x, tm_w;
   int rc;
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTileRows))) return rc;
@@ -563,17 +565,18 @@ int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, 
   p.B = B; p.N = N; p.D = D; p.M = M; p.J = pl.J; p.ntiles = pl.ntiles; p.G = pl.G; p.ngroups = pl.ngroups;
   p.nchunks = D / kChunkD; p.nstages = pl.ks_stages; p.w_batched = w_batched; p.nbuf = pl.ks_nbuf;
   p.bufcols = pl.G * pl.J; p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
-  p.out = out; p.S = S; p.rmax = rmax; p.rsum = rsum; p.delta = delta;
+  p.nkb = pl.nkb; p.ndelta = ndelta;
+  p.out = out; p.blocks = blocks; p.S = S; p.rmax = rmax; p.rsum = rsum; p.delta = delta;
   if ((rc = set_dyn_smem(ks_kernel<kMode>, pl.ks_smem))) return rc;
   const int grid = std::min(B * pl.ngroups, kNumSMs);
-  ks_kernel<kMode><<<grid, 256, pl.ks_smem, s>>>(tm_x, tm_w, p);
+  ks_kernel<kMode><<<grid, kThreads, pl.ks_smem, s>>>(tm_x, tm_w, p);
   EP_LAUNCH_CHECK();
   return 0;
 }
 
 template <int kMode>
-int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const float* src, const float* rmax,
-              const float* rsum, float* out, int* groups_out, int round_out, cudaStream_t s) {
+int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const uint8_t* blocks, const float* rsum,
+              float* out, int* groups_out, int round_out, cudaStream_t s) {
   CUtensorMap tm_x;
   int rc;
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTokBlock))) return rc;
@@ -586,13 +589,13 @@ int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const f
   p.bufcols = p.nsl * pl.J;
   p.nbuf = (kMode == 0 && 2 * p.bufcols <= 512) ? 2 : 1;
   p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
-  p.src = src; p.rmax = rmax; p.rsum = rsum; p.out = out;
+  p.blocks = blocks; p.rsum = rsum; p.out = out;
   p.debug = g_debug;
   p.round_out = round_out;
   if ((rc = set_dyn_smem(kp_kernel<kMode>, pl.kp_smem))) return rc;
   const int gx = std::max(1, std::min(B, kNumSMs / ysplit));
   if (groups_out) *groups_out = gx;
-  kp_kernel<kMode><<<dim3(gx, ysplit), 384, pl.kp_smem, s>>>(tm_x, p);
+  kp_kernel<kMode><<<dim3(gx, ysplit), kThreads, pl.kp_smem, s>>>(tm_x, p);
   EP_LAUNCH_CHECK();
   return 0;
 }
@@ -616,40 +619,53 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   const Ws100 w = carve100(B, N, D, M, pl);
   __nv_bfloat16* qhl = (__nv_bfloat16*)((char*)ws + w.qhl);
+  uint8_t* blocks = (uint8_t*)ws + w.dS;
   int rc;
   StageTimer tm(s);
   split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
   EP_LAUNCH_CHECK();
   tm.mark("split_q");
-  if ((rc = launch_ks<0>(x, qhl, 0, B, N, D, M, pl, S, nullptr, nullptr, nullptr, nullptr, s))) return rc;
+  if ((rc = launch_ks<0>(x, qhl, 0, B, N, D, M, pl, S, nullptr, nullptr, nullptr, nullptr, nullptr, 0, s))) return rc;
   tm.mark("ks<0> logits");
-  const long long rows = (long long)B * M;
-  rowstats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, rows, N, rowmax, rowsum, attn);
+  const long long rows = (long long)B * (pl.J / 2);
+  rowstats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, B, M, pl.J, N, pl.nkb, rowmax, rowsum, attn,
+                                                            P ? blocks : nullptr);
   EP_LAUNCH_CHECK();
   tm.mark("rowstats");
   if (P == nullptr) return 0;
-  rc = launch_kp<0>(x, B, N, D, M, pl, S, rowmax, rowsum, P, nullptr, round_p, s);
+  rc = launch_kp<0>(x, B, N, D, M, pl, blocks, rowsum, P, nullptr, round_p, s);
   tm.mark("kp<0> pool");
   return rc;
 }
 
+// dP arrives as bf16 hi/lo rows (B, J, D) in the workspace (written by the projection backward) together
+// with `ndelta` partial sums of delta = dP . P
+void* sm100_dphl_ptr(void* ws, int B, int N, int D, int M) {
+  const Plan pl = make_plan(N, D, M);
+  return (char*)ws + carve100(B, N, D, M, pl).dphl;
+}
+int sm100_J(int N, int D, int M) { return make_plan(N, D, M).J; }
+
 int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int D, int M, const float* rowmax,
-                   const float* rowsum, const float* dP, const float* delta, float* d_cls, void* ws, cudaStream_t s) {
+                   const float* rowsum, const float* dP, const float* delta, int ndelta, float* d_cls, void* ws,
+                   cudaStream_t s) {
   const Plan pl = make_plan(N, D, M);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   const Ws100 w = carve100(B, N, D, M, pl);
   __nv_bfloat16* dphl = (__nv_bfloat16*)((char*)ws + w.dphl);
-  float* dS = (float*)((char*)ws + w.dS);
+  uint8_t* blocks = (uint8_t*)ws + w.dS;
   float* part = (float*)((char*)ws + w.part);
   int rc;
   StageTimer tm(s);
-  split_hilo_kernel<<<dim3(std::max(1, std::min(64, pl.J * D / 8 / 256)), B), 256, 0, s>>>(dP, 1.f, M, pl.J, D, dphl);
-  EP_LAUNCH_CHECK();
-  tm.mark("split_dP");
-  if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, dS, S, rowmax, rowsum, delta, s))) return rc;
+  if (dP) {   // fp32 dP (B, M, D) given: split it here; nullptr = the hi/lo rows are already in the workspace
+    split_hilo_kernel<<<dim3(std::max(1, std::min(64, pl.J * D / 8 / 256)), B), 256, 0, s>>>(dP, 1.f, M, pl.J, D, dphl);
+    EP_LAUNCH_CHECK();
+    tm.mark("split_dP");
+  }
+  if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, nullptr, blocks, S, rowmax, rowsum, delta, ndelta, s))) return rc;
   tm.mark("ks<1> dS");
   int groups = 0;
-  if ((rc = launch_kp<1>(x, B, N, D, M, pl, dS, nullptr, nullptr, part, &groups, 0, s))) return rc;
+  if ((rc = launch_kp<1>(x, B, N, D, M, pl, blocks, nullptr, part, &groups, 0, s))) return rc;
   tm.mark("kp<1> dq");
   const size_t n = (size_t)M * D;
   reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, groups, n, scale, d_cls);
