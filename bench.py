@@ -11,10 +11,10 @@ batch that is already resident in HBM; batches cycle through a pool of `--pool` 
 (8 x 539 MB >> 126 MB L2, so every step streams its tokens from HBM).  Weak scaling: per-GPU batch fixed.
 
 One JSON line on stdout (rank 0).  Extra keys next to the contract's:
-  roofline      the token-streaming backward kernel (ep_bwd_pool, the dominant kernel) timed alone with
-                CUDA events; achieved = B*N*D*2 bytes / duration (algorithmic bytes: each bf16 token
-                read once); peak = MEASURED_PEAKS.json hbm_gbs.
-  roofline_fwd  same for the forward pooling kernel (ep_fwd's streaming part).
+  roofline      the slowest of the four token-streaming kernels (ks<0> logits, kp<0> pool, ks<1> dS,
+                kp<1> dq), each timed with CUDA events on its launching stream; achieved = B*N*D*2 bytes
+                (algorithmic: each bf16 token read once per kernel, SURVEY.md 8d) / duration;
+                peak = MEASURED_PEAKS.json hbm_gbs.  roofline_all_streaming_kernels lists all four.
   step_roofline_frac   (2*B*N*D*2 bytes / step time) / peak -- the whole step against the roofline.
   cpu_baseline  the oracle (CPU restatement of the reference head, torch fp32, all host threads) on a
                 bounded sample of the same workload.
@@ -264,55 +264,54 @@ def main():
     h2d = B * N * D * 2 + B * 8
     d2h = 4
 
-    # ---------------- the dominant kernels alone (rank 0's GPU), for the roofline ----------------
+    # ---------------- the token-streaming kernels alone (rank 0's GPU), for the roofline ----------------
+    # ep_fwd / ep_bwd_pool are replayed outside the graph with the library's per-kernel CUDA-event timers on
+    # (ep_set_debug(32): events recorded on the launching stream around every kernel of the call).  Each of
+    # the four streaming kernels reads the bf16 tokens of the batch exactly once, so its algorithmic bytes
+    # per launch are B*N*D*2 (2*D bytes per token per pass).
     peak, peak_src = peaks()
-    alg_bytes = B * N * D * 2                                    # one pass over the bf16 tokens
+    alg_bytes = B * N * D * 2
     pool_mod, s = head[0], E._lib.stream_ptr(dev)
     xt = E._lib.x_dtype_code(pool_x[0])
-
-    def fwd(i):
-        x = pool_x[i % args.pool]
+    lib.ep_set_debug(32)
+    E._lib.kernel_timings()
+    reps = 6
+    for i in range(reps + 2):
+        x = pool_x[i % args.pool]                                  # rotating the pool is the L2 flush
         E._lib.check(lib.ep_fwd(x.data_ptr(), xt, pool_mod.cls_token.data_ptr(), pool_mod.v.weight.data_ptr(), None,
-                                float(pool_mod.scale), B, N, D, M, 1, tr.out.data_ptr(), tr.S.data_ptr(), tr.rowmax.data_ptr(),
-                                tr.rowsum.data_ptr(), tr.P.data_ptr(), None, tr.ws.data_ptr(), tr.ws.numel(), s), "ep_fwd")
-
-    def bwd_pool(i):
-        x = pool_x[i % args.pool]
+                                float(pool_mod.scale), B, N, D, M, 1, tr.out.data_ptr(), tr.S.data_ptr(),
+                                tr.rowmax.data_ptr(), tr.rowsum.data_ptr(), tr.P.data_ptr(), None, tr.ws.data_ptr(),
+                                tr.ws.numel(), s), "ep_fwd")
+        E._lib.check(lib.ep_bwd_proj(tr.dout.data_ptr(), tr.P.data_ptr(), pool_mod.v.weight.data_ptr(), B, N, D, M, 1,
+                                     tr.g["v_w"].data_ptr(), None, tr.ws.data_ptr(), tr.ws.numel(), s), "ep_bwd_proj")
         E._lib.check(lib.ep_bwd_pool(x.data_ptr(), xt, pool_mod.cls_token.data_ptr(), float(pool_mod.scale), B, N, D, M,
-                                     1, tr.S.data_ptr(), tr.rowmax.data_ptr(), tr.rowsum.data_ptr(), tr.g["cls"].data_ptr(),
-                                     tr.ws.data_ptr(), tr.ws.numel(), s), "ep_bwd_pool")
-
-    def proj(i):                                                  # ep_fwd minus its streaming kernel
-        pass
-
-    noflush = lambda i: None                                      # rotating the pool IS the flush (8 x 539 MB >> L2)
-    t_fwd_all = time_kernel(fwd, 10, noflush)
-    t_bwd = time_kernel(bwd_pool, 10, noflush)
+                                     1, tr.S.data_ptr(), tr.rowmax.data_ptr(), tr.rowsum.data_ptr(),
+                                     tr.g["cls"].data_ptr(), tr.ws.data_ptr(), tr.ws.numel(), s), "ep_bwd_pool")
+        if i == 1:
+            E._lib.kernel_timings()                                # drop the warm-up records
     fam = lib.ep_last_kernel_family()
-    # ep_fwd = streaming kernel + the small projection GEMM; time the GEMM part by calling it on a 1-token input
-    x1 = torch.zeros(B, 1, D, device=dev, dtype=torch.bfloat16)
-    ws1 = torch.empty(max(16, lib.ep_workspace_bytes(B, 1, D, M, 1)), dtype=torch.uint8, device=dev)
-
-    def fwd_small(i):
-        E._lib.check(lib.ep_fwd(x1.data_ptr(), xt, pool_mod.cls_token.data_ptr(), pool_mod.v.weight.data_ptr(), None,
-                                float(pool_mod.scale), B, 1, D, M, 1, tr.out.data_ptr(), tr.S.data_ptr(), tr.rowmax.data_ptr(),
-                                tr.rowsum.data_ptr(), tr.P.data_ptr(), None, ws1.data_ptr(), ws1.numel(), s), "ep_fwd")
-    t_proj = time_kernel(fwd_small, 10, noflush)
-    t_fwd = max(t_fwd_all - t_proj, 1e-6)
-    roof = lambda t: {"bound": "hbm", "achieved": alg_bytes / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                      "frac": alg_bytes / (t * 1e-3) / 1e9 / peak, "traffic": None, "kernel_ms": t}
+    lib.ep_set_debug(0)
+    agg = {}
+    for nm, us in E._lib.kernel_timings():
+        agg.setdefault(nm, []).append(us)
+    kernels = {k: sum(v) / len(v) for k, v in agg.items()}
+    streaming = {k: v for k, v in kernels.items() if k.startswith(("ks<", "kp<", "pool_"))}
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    r_bwd, r_fwd = roof(t_bwd), roof(t_fwd)
-    r_bwd["kernel"] = "ep_bwd_pool (token-streaming backward), family %d" % fam
-    r_fwd["kernel"] = "ep_fwd pooling kernel (token-streaming forward), family %d" % fam
-    key = f"{args.config}_M{M}_family{fam}"
-    r_bwd["traffic"] = traffic.get(key, {}).get("bwd")
-    r_fwd["traffic"] = traffic.get(key, {}).get("fwd")
-    r_bwd["peak_source"] = r_fwd["peak_source"] = peak_src
+    tkey = f"{args.config}_M{M}"
+
+    def roof(name, us):
+        ach = alg_bytes / (us * 1e-6) / 1e9
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(tkey, {}).get(name), "kernel_us": us, "algorithmic_bytes": alg_bytes,
+                "peak_source": peak_src}
+    per_kernel = {k: roof(k, v) for k, v in streaming.items()}
+    dominant = max(streaming, key=streaming.get) if streaming else None
+    r_dom = per_kernel[dominant] if dominant else {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s",
+                                                    "frac": None, "traffic": None}
 
     if rank != 0:
         if world > 1:
@@ -331,7 +330,8 @@ def main():
                     "ms_per_step": float(ms2) / e2e_steps},
             "gpu_launches": (tr.launches_per_step or 0) * args.steps,
             "launches_per_step": tr.launches_per_step,
-            "roofline": r_bwd, "roofline_fwd": r_fwd,
+            "roofline": r_dom, "roofline_all_streaming_kernels": per_kernel,
+            "kernel_us": {k: round(v, 1) for k, v in kernels.items()},
             "step_roofline_frac": (2 * alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak,
             "mean_loss": loss}
     if not args.no_cpu_baseline:

@@ -26,6 +26,9 @@ _SIGNATURES = {
     "ep_set_gemm_mode": (c_int, [c_int]),
     "ep_launch_count": (ctypes.c_ulonglong, []),
     "ep_set_debug": (c_int, [c_int]),
+    "ep_timing_count": (c_int, []),
+    "ep_timing_get": (c_int, [c_int, ctypes.c_char_p, c_int, ctypes.POINTER(c_float)]),
+    "ep_timing_reset": (c_int, []),
     "ep_kernel_family_for": (c_int, [c_int] * 5),
     "ep_workspace_bytes": (c_size_t, [c_int] * 5),
     "ep_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 5 +
@@ -80,6 +83,20 @@ def check(code, what):
     if code < 0:
         raise ValueError(f"{what}: {msg} (ep_status {code})")
     raise EPError(f"{what}: CUDA error {code}: {msg}")
+
+
+def kernel_timings(reset=True):
+    """[(kernel name, microseconds)] recorded since the last reset (needs ep_set_debug(32))."""
+    lib = load()
+    out = []
+    buf = ctypes.create_string_buffer(32)
+    us = c_float()
+    for i in range(lib.ep_timing_count()):
+        if lib.ep_timing_get(i, buf, 32, ctypes.byref(us)) == 0:
+            out.append((buf.value.decode(), float(us.value)))
+    if reset:
+        lib.ep_timing_reset()
+    return out
 
 
 def ptr(t):

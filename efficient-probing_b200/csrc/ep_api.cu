@@ -48,6 +48,16 @@ extern "C" int ep_set_gemm_mode(int mode) {
   return 0;
 }
 extern "C" int ep_set_debug(int flags) { ep::g_debug = flags; return 0; }
+ep::TimingRecord ep::g_timings[32];
+int ep::g_ntimings = 0;
+extern "C" int ep_timing_count(void) { return ep::g_ntimings; }
+extern "C" int ep_timing_get(int i, char* name, int name_len, float* us) {
+  if (i < 0 || i >= ep::g_ntimings || !name || !us || name_len < 1) return EP_ERR_SHAPE;
+  snprintf(name, (size_t)name_len, "%s", ep::g_timings[i].name);
+  *us = ep::g_timings[i].us;
+  return 0;
+}
+extern "C" int ep_timing_reset(void) { ep::g_ntimings = 0; return 0; }
 extern "C" int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M) {
   if (g_kernel_mode == 1) return 1;
   return sm100_supported(x_dtype, B, N, D, M) ? 2 : (g_kernel_mode == 2 ? 0 : 1);

@@ -69,6 +69,9 @@ __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpr
 
 extern int g_debug;
 // developer aid (ep_set_debug bit 5): CUDA-event time of every kernel of one call, printed to stderr
+struct TimingRecord { char name[24]; float us; };
+extern TimingRecord g_timings[32];
+extern int g_ntimings;
 struct StageTimer {
   bool on; cudaStream_t s; cudaEvent_t ev[12]; const char* name[12]; int n = 0;
   StageTimer(cudaStream_t st) : on((g_debug & 32) != 0), s(st) { if (on) mark("start"); }
@@ -81,12 +84,15 @@ struct StageTimer {
     cudaStreamSynchronize(s);
     for (int i = 1; i < n; ++i) {
       float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      fprintf(stderr, "[ep timing] %-18s %8.1f us\n", name[i], ms * 1e3f);
+      if (g_debug & 256) fprintf(stderr, "[ep timing] %-18s %8.1f us\n", name[i], ms * 1e3f);
+      if (g_ntimings < 32) {
+        snprintf(g_timings[g_ntimings].name, sizeof(g_timings[0].name), "%s", name[i]);
+        g_timings[g_ntimings++].us = ms * 1e3f;
+      }
     }
     for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
   }
 };
-
 
 // ---- internal launchers shared between translation units (all return ep_status / cudaError) ----
 struct GemmDesc {      // C[z][i][j] = sum_k A[z][i][k] * B[z][k][j] (+ bias[z][j]); element strides

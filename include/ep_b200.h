@@ -54,8 +54,14 @@ int ep_set_kernel_mode(int mode);
 int ep_set_gemm_mode(int mode);
 /* Which family the last ep_fwd/ep_bwd call on this thread used (1 = general, 2 = tcgen05). */
 int ep_last_kernel_family(void);
-/* Developer knob for performance experiments (results are WRONG when non-zero); 0 in normal use. */
+/* Developer knob: bit 5 (32) makes ep_fwd / ep_bwd_proj / ep_bwd_pool bracket each of their kernels with
+ * CUDA events on the call's stream (one host sync per call) and record the durations, read back with
+ * ep_timing_*; bit 8 (256) also prints them.  Other bits are performance experiments that make the
+ * results WRONG.  0 in normal use. */
 int ep_set_debug(int flags);
+int ep_timing_count(void);
+int ep_timing_get(int i, char* name, int name_len, float* microseconds);
+int ep_timing_reset(void);
 /* Which family ep_fwd/ep_bwd would use for this shape under the current mode (0 = none: forced tcgen05
  * but unsupported). */
 int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M);

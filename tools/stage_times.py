@@ -49,6 +49,11 @@ for name, fn in stages.items():
     torch.cuda.synchronize()
     res[name] = round(sum(e0.elapsed_time(e1) for e0, e1 in ev) / a.iters * 1e3, 1)
 res["total_us"] = round(sum(res.values()), 1)
+if a.debug & 32:
+    agg = {}
+    for nm, us in _lib.kernel_timings():
+        agg.setdefault(nm, []).append(us)
+    res["kernels_us"] = {k: round(sum(v[-a.iters:]) / len(v[-a.iters:]), 1) for k, v in agg.items()}
 res["family"] = lib.ep_last_kernel_family()
 res["shape"] = [B, N, D, M, K]
 print(json.dumps(res))
