@@ -11,6 +11,7 @@ from .ep import EfficientProbing, EPPoolFunction, ep_attention                  
 from .probe_heads import build_probe_head, make_ep_head, POOLINGS                    # noqa: F401
 from .optim import LARS, adjust_learning_rate                                        # noqa: F401
 from .trainer import EPHeadTrainer                                                   # noqa: F401
+from .flatgrad import FlatGradLayout, shard_range, allreduce_sum_                    # noqa: F401
 from . import _lib                                                                   # noqa: F401
 
 __all__ = ["EfficientProbing", "EPPoolFunction", "ep_attention", "build_probe_head", "make_ep_head", "POOLINGS",

@@ -24,6 +24,7 @@ from torch import nn
 
 from . import _lib
 from .ep import EfficientProbing
+from .flatgrad import FlatGradLayout, allreduce_sum_
 from .optim import lars_launch
 
 BN_EPS_DEFAULT = 1e-6
@@ -66,17 +67,11 @@ class EPHeadTrainer:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise TypeError("head parameters must be contiguous fp32")
         self.trust = [p.ndim > 1 for p in self.params]                                   # util/lars.py:21
-        # flat gradient buffer: large, early-ready tensors first, cls_token last
-        sizes = {"fc_w": K * Dp, "fc_b": K, "v_w": Dp * D, "v_b": Dp if pool.v.bias is not None else 0, "cls": M * D}
-        # every slice starts on a 256-byte boundary (vector stores / TMA in the kernels); the padding is zero
-        pad = lambda n: (n + 63) // 64 * 64
-        self.flat_grad = torch.zeros(sum(pad(n) for n in sizes.values()), **f32)
-        off, self.g = 0, {}
-        for k, n in sizes.items():
-            self.g[k] = self.flat_grad[off:off + n]
-            off += pad(n)
-        off -= pad(sizes["cls"]) - sizes["cls"]
-        self.n_early = off - sizes["cls"]
+        # flat gradient buffer: large, early-ready tensors first, cls_token last (flatgrad.py)
+        self.layout = FlatGradLayout(K, Dp, D, M, pool.v.bias is not None)
+        self.flat_grad = self.layout.allocate(dev)
+        self.g = self.layout.views(self.flat_grad)
+        self.n_early = self.layout.early
         self.grads = [self.g["cls"], self.g["v_w"]] + ([self.g["v_b"]] if pool.v.bias is not None else []) + \
                      [self.g["fc_w"], self.g["fc_b"]]
         self.mus = [torch.zeros_like(p) for p in self.params]
@@ -152,17 +147,17 @@ class EPHeadTrainer:
             cur = torch.cuda.current_stream(self.dev)
             self.comm_stream.wait_stream(cur)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(self.flat_grad[:self.n_early], group=self.group)
+                allreduce_sum_(self.flat_grad, self.group, 0, self.n_early)
         _lib.check(lib.ep_bwd_pool(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
                                    float(pool.scale), B, N, D, M, self.d_out, self.S.data_ptr(),
                                    self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.g["cls"].data_ptr(), self.ws.data_ptr(),
                                    self.ws.numel(), s), "ep_bwd_pool")
         if self.world > 1:
             if self.overlap_comm:
-                dist.all_reduce(self.flat_grad[self.n_early:], group=self.group)
+                allreduce_sum_(self.flat_grad, self.group, self.n_early)
                 torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
             else:
-                dist.all_reduce(self.flat_grad, group=self.group)
+                allreduce_sum_(self.flat_grad, self.group)
         lars_launch(self.params, self.grads, self.mus, self.trust, self.hyper, self.lars_scratch)
         self.loss_sum.add_(self.step_loss)
 
