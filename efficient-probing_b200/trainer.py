@@ -124,7 +124,9 @@ class EPHeadTrainer:
                                      self.logits.data_ptr(), self.lin_ws.data_ptr(), self.lin_ws.numel(), s),
                    "ep_linear_fwd")
 
-    def _step_body(self):
+    # The step in three stream-ordered parts; the gradient exchange sits between them.
+    def _part1(self):
+        """forward, loss, and every gradient that does not need the tokens again"""
         lib, s = self.lib, _lib.stream_ptr(self.dev)
         B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
         pool, fc = self.pool, self.fc
@@ -142,24 +144,44 @@ class EPHeadTrainer:
         _lib.check(lib.ep_bwd_proj(self.dout.data_ptr(), self.P.data_ptr(), pool.v.weight.data_ptr(), B, N, D, M,
                                    self.d_out, self.g["v_w"].data_ptr(), d_vb, self.ws.data_ptr(), self.ws.numel(), s),
                    "ep_bwd_proj")
-        if self.overlap_comm:
-            # the first n_early floats are final: reduce them underneath the token-streaming half
-            cur = torch.cuda.current_stream(self.dev)
-            self.comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self.comm_stream):
-                allreduce_sum_(self.flat_grad, self.group, 0, self.n_early)
+
+    def _part2(self):
+        """token-streaming half of the backward pass: d cls_token"""
+        lib, s = self.lib, _lib.stream_ptr(self.dev)
+        pool = self.pool
         _lib.check(lib.ep_bwd_pool(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
-                                   float(pool.scale), B, N, D, M, self.d_out, self.S.data_ptr(),
-                                   self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.g["cls"].data_ptr(), self.ws.data_ptr(),
-                                   self.ws.numel(), s), "ep_bwd_pool")
-        if self.world > 1:
-            if self.overlap_comm:
-                allreduce_sum_(self.flat_grad, self.group, self.n_early)
-                torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
-            else:
-                allreduce_sum_(self.flat_grad, self.group)
+                                   float(pool.scale), self.B, self.N, self.D, self.M, self.d_out, self.S.data_ptr(),
+                                   self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.g["cls"].data_ptr(),
+                                   self.ws.data_ptr(), self.ws.numel(), s), "ep_bwd_pool")
+
+    def _part3(self):
         lars_launch(self.params, self.grads, self.mus, self.trust, self.hyper, self.lars_scratch)
         self.loss_sum.add_(self.step_loss)
+
+    def _exchange_early(self):
+        """[fc, v] gradients are final after part 1: reduce them underneath part 2 on the comm stream"""
+        if self.world == 1:
+            return
+        if self.overlap_comm:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(self.comm_stream):
+                allreduce_sum_(self.flat_grad, self.group, 0, self.n_early)
+
+    def _exchange_rest(self):
+        if self.world == 1:
+            return
+        if self.overlap_comm:
+            allreduce_sum_(self.flat_grad, self.group, self.n_early)
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+        else:
+            allreduce_sum_(self.flat_grad, self.group)
+
+    def _step_body(self):
+        self._part1()
+        self._exchange_early()
+        self._part2()
+        self._exchange_rest()
+        self._part3()
 
     def _run(self):
         if not self.use_graph:
@@ -171,11 +193,11 @@ class EPHeadTrainer:
                 self._step_body()
             return
         key = (self._cx.data_ptr(), self._ct.data_ptr())
-        graph = self.graphs.get(key)
-        if graph is None:
-            snap = self._snapshot()
+        graphs = self.graphs.get(key)
+        if graphs is None:
             if not self.graphs:
                 # one eager step on a side stream first (lazy module loading, NCCL communicator set-up)
+                snap = self._snapshot()
                 side = torch.cuda.Stream(device=self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
                 with torch.cuda.stream(side):
@@ -185,12 +207,25 @@ class EPHeadTrainer:
                 torch.cuda.current_stream(self.dev).wait_stream(side)
                 torch.cuda.synchronize(self.dev)
                 self._restore(snap)
-            graph = torch.cuda.CUDAGraph()
-            mode = "thread_local" if self.world > 1 else "global"
-            with torch.cuda.graph(graph, capture_error_mode=mode):
-                self._step_body()
-            self.graphs[key] = graph
-        graph.replay()
+            # single GPU: the whole step is one graph.  Multi-GPU: the NCCL all-reduces stay outside the
+            # graphs (three graphs per step with the two exchanges between them) -- capturing the
+            # collectives inside a graph deadlocked on this stack, and the eager calls cost microseconds.
+            parts = [self._step_body] if self.world == 1 else [self._part1, self._part2, self._part3]
+            graphs = []
+            for part in parts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    part()
+                graphs.append(g)
+            self.graphs[key] = graphs
+        if self.world == 1:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            self._exchange_early()
+            graphs[1].replay()
+            self._exchange_rest()
+            graphs[2].replay()
 
     def _snapshot(self):
         bn = self.bn
