@@ -72,6 +72,8 @@ struct Ws {                      // workspace layout
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
 bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !(ep::g_debug & 128); }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
+int dp_nt(int D) { return std::min(128, (D + 31) / 32 * 32); }     // column tile of the fused dP GEMM
+int col_tiles(int D) { return (D + dp_nt(D) - 1) / dp_nt(D); }
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
@@ -79,7 +81,7 @@ Ws carve(int B, int N, int D, int M) {
   w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
   w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
-  w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
+  w.delta = off; off += align_up((size_t)32 * B * M * sizeof(float), 256);   // up to 32 column-tile partials
   w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
   w.sm100 = off; off += align_up(sm100_workspace_bytes(B, N, D, M), 256);
   w.total = off;
@@ -144,8 +146,8 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   return launch_gemm_v0(g, s);
 }
 
-extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int B, int N, int D, int M,
-                           int d_out, float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes,
+extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int x_dtype, int B, int N, int D,
+                           int M, int d_out, float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes,
                            void* stream) {
   if (!g_out || !P || !v_w || !d_v_w) return EP_ERR_NULL;
   if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
@@ -172,6 +174,19 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
       const unsigned long long c3 = 3ull * c;
       TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1};
       TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1};
+      int fam_rc = 0;
+      if (use_sm100(x_dtype, B, N, D, M, &fam_rc) && col_tiles(D) <= 32) {
+        // tcgen05 pooling kernels follow: the GEMM epilogue emits what they consume -- dP as bf16 hi/lo operand
+        // rows and delta = dP . P as per-column-tile partials -- and fp32 dP is never written
+        void* sm = (char*)workspace + w.sm100;
+        const int J = sm100_J(N, D, M);
+        void* hl = sm100_dphl_ptr(sm, B, N, D, M);
+        if (J != 2 * M) EP_CUDA(cudaMemsetAsync(hl, 0, (size_t)B * J * D * 2, s));
+        if ((rc = tc_gemm_dp(A, Bm, B, D, 3 * c, M, dp_nt(D), P, hl, delta, J, s))) return rc;
+        tm.mark("dP tc-gemm+hl");
+        return 0;
+      }
+      if (fam_rc) return fam_rc;
       if ((rc = tc_gemm(A, Bm, B, D, 3 * c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
       tm.mark("dP tc-gemm");
     }
@@ -215,8 +230,10 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
   float* slots = (float*)((char*)workspace + w.slots);
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
-    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, dP, delta, 1, d_cls_token,
-                          (char*)workspace + w.sm100, s);
+    const int c = D / d_out / M;
+    const bool fused = use_tc() && c % 4 == 0 && col_tiles(D) <= 32;      // what ep_bwd_proj did (same predicate)
+    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, fused ? nullptr : dP, delta,
+                          fused ? col_tiles(D) : 1, d_cls_token, (char*)workspace + w.sm100, s);
   }
   if (rc) return rc;
   t_last_family = 1;
@@ -231,7 +248,8 @@ extern "C" int ep_bwd(const void* x, int x_dtype, const float* cls_token, const 
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
   if (!v_w || !S || !rowmax || !rowsum || !P || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
-  if ((rc = ep_bwd_proj(g_out, P, v_w, B, N, D, M, d_out, d_v_w, d_v_b, workspace, workspace_bytes, stream))) return rc;
+  if ((rc = ep_bwd_proj(g_out, P, v_w, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace, workspace_bytes, stream)))
+    return rc;
   return ep_bwd_pool(x, x_dtype, cls_token, scale, B, N, D, M, d_out, S, rowmax, rowsum, d_cls_token, workspace,
                      workspace_bytes, stream);
 }

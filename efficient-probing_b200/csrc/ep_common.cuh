@@ -130,6 +130,10 @@ int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias,
                     long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z,
                     long long bias_z, cudaStream_t s);
 
+// projection backward with the fused epilogue: dP as bf16 hi/lo rows (B, Jrows, D) + ceil(J/NT) partial deltas
+int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, const float* P, void* hl,
+               float* delta_part, int Jrows, cudaStream_t s);
+
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s);
 int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,

@@ -8,6 +8,7 @@
 // contiguous); the same 128-byte-swizzled shared-memory bytes serve both through the descriptor's
 // major bit, so no operand is ever transposed or converted on the way.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <algorithm>
 
@@ -29,6 +30,15 @@ struct GemmTC {
   float* C; const float* bias;
   long long c_row, c_col, c_z, bias_z;        // element strides of C and bias
   int round_tf32;                             // round the stored result to tf32 (it feeds another TF32 GEMM)
+  int stages;                                 // smem ring depth (<= kGStages; short contractions use fewer)
+  // epilogue mode 1 (projection backward, C = dP[b, z=m, d]): instead of storing fp32 dP, write it as the
+  // bf16 hi/lo operand rows (B, Jrows, D) the dA kernel consumes and the partial delta = sum_d dP * P of this
+  // column tile -- dP never touches memory in fp32
+  int epi_mode;
+  const float* P;                             // (B, Mq, D)
+  __nv_bfloat16* hl;                          // (B, Jrows, D)
+  float* delta_part;                          // (gridDim.x, B * Mq)
+  int Mq, Jrows;
 };
 
 __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
@@ -59,7 +69,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t a_bytes = 128u * 128u;                       // 128 rows (or 4 atoms x 32 k-rows) x 128 B
   const uint32_t b_bytes = (uint32_t)g.NT * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t bar_base = smem_base + kGStages * stage_bytes;
+  const uint32_t bar_base = smem_base + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kGStages + s); };
   const uint32_t done_bar = bar_base + 8u * (2 * kGStages);
@@ -68,7 +78,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t tmem_cols = g.NT <= 32 ? 32 : g.NT <= 64 ? 64 : g.NT <= 128 ? 128 : 256;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < g.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
@@ -106,7 +116,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tma_load_3d(bdst + (uint32_t)a * 4096u, &tm_b, full_bar(s), j0 + 32 * a, g.b_swap ? zb : k0,
                         g.b_swap ? k0 : zb);
         }
-        if (++s == kGStages) { s = 0; ph ^= 1u; }
+        if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -127,7 +137,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kc | k) != 0));
         }
         umma_commit(empty_bar(s));
-        if (++s == kGStages) { s = 0; ph ^= 1u; }
+        if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
       umma_commit(done_bar);
     }
@@ -139,6 +149,51 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16);
     float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
     const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
+    if (g.epi_mode == 1) {
+      // row = sample b, z = query m, columns = d (J == D)
+      const float* prow = g.P + ((size_t)row * g.Mq + z) * g.J;
+      __nv_bfloat16* hrow = g.hl + ((size_t)row * g.Jrows + 2 * z) * g.J;
+      float dsum = 0.f;
+      const bool rok = row < g.I;
+      float4 pv[2][4];
+      auto load_p = [&](int c0, float4 (&dst)[4]) {
+        const int col = j0 + c0;
+        if (rok && c0 < g.NT && col + 16 <= g.J) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(prow + col) + q);
+        }
+      };
+      auto emit = [&](int c0, const float4 (&src)[4]) {
+        uint32_t r[16];
+        tmem_ld16(acc + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int col = j0 + c0;
+        if (rok && col + 16 <= g.J) {
+          const float* pf = reinterpret_cast<const float*>(src);
+          __align__(16) __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v = __uint_as_float(r[i]);
+            dsum = fmaf(v, pf[i], dsum);
+            hi[i] = __float2bfloat16_rn(v);
+            lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
+          }
+          reinterpret_cast<uint4*>(hrow + col)[0] = reinterpret_cast<const uint4*>(hi)[0];
+          reinterpret_cast<uint4*>(hrow + col)[1] = reinterpret_cast<const uint4*>(hi)[1];
+          reinterpret_cast<uint4*>(hrow + g.J + col)[0] = reinterpret_cast<const uint4*>(lo)[0];
+          reinterpret_cast<uint4*>(hrow + g.J + col)[1] = reinterpret_cast<const uint4*>(lo)[1];
+        }
+      };
+      // the P loads of the next 16 columns are in flight while the current ones are converted
+      load_p(0, pv[0]);
+      for (int c0 = 0; c0 < g.NT; c0 += 32) {
+        load_p(c0 + 16, pv[1]);
+        emit(c0, pv[0]);
+        load_p(c0 + 32, pv[0]);
+        if (c0 + 16 < g.NT) emit(c0 + 16, pv[1]);
+      }
+      if (row < g.I) g.delta_part[(size_t)blockIdx.x * g.I * g.Mq + (size_t)row * g.Mq + z] = dsum;
+    } else {
     const bool vec = g.c_col == 1 && (g.c_row % 4) == 0 && (g.c_z % 4) == 0 && (j0 % 4) == 0 &&
                      ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     for (int c0 = 0; c0 < g.NT; c0 += 16) {
@@ -168,6 +223,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -218,10 +274,11 @@ int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, ui
 }
 
 bool gemm_tc_available() { return encode_fn() != nullptr; }
-int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTC& g, int Z, cudaStream_t s);
+int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s);
 
-int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTC& g, int Z, cudaStream_t s) {
-  const size_t smem = (size_t)kGStages * (128 * 128 + (size_t)g.NT * 128) + 1024 + 256;
+int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s) {
+  g.stages = std::max(1, std::min(kGStages, (g.K + kGK - 1) / kGK));
+  const size_t smem = (size_t)g.stages * (128 * 128 + (size_t)g.NT * 128) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -237,6 +294,20 @@ static int side_tmap(CUtensorMap* m, const TcSide& sd, int tile_rows) {
   // K-major: box = 32 k x tile_rows rows; MN-major: box = 32 mn x 32 k-rows
   const uint32_t r = sd.mn_major ? 32u : (uint32_t)tile_rows;
   return make_tmap_f32(m, sd.base, sd.d0, sd.d1, sd.d2, sd.s1, sd.s2, sd.swap ? 1u : r, sd.swap ? r : 1u);
+}
+
+int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, const float* P, void* hl,
+               float* delta_part, int Jrows, cudaStream_t s) {
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = side_tmap(&ta, A, 128))) return rc;
+  if ((rc = side_tmap(&tb, B, NT))) return rc;
+  GemmTC g{};
+  g.I = I; g.J = J; g.K = K; g.NT = NT;
+  g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
+  g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
+  g.epi_mode = 1; g.P = P; g.hl = (__nv_bfloat16*)hl; g.delta_part = delta_part; g.Mq = Z; g.Jrows = Jrows;
+  return launch_gemm_tc(ta, tb, g, Z, s);
 }
 
 int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,

@@ -310,7 +310,7 @@ int launch_split3_transpose(const float* src, float* dst, int K, int R, int Z, l
 // in registers: for the one product whose A operand (the pooled tokens P, B*M*D floats) is too large
 // to copy.  mma.sync m16n8k8, cp.async pipeline, 64 x 32 tile (the per-query projection is 32 wide).
 // ------------------------------------------------------------------------------------------------
-constexpr int NT_BI = 64, NT_BJ = 32, NT_BK = 32, NT_LD = NT_BK + 4, NT_STAGES = 4;
+constexpr int NT_BI = 128, NT_BJ = 32, NT_BK = 32, NT_LD = NT_BK + 4, NT_STAGES = 3;
 constexpr int NT_STAGE_FLOATS = (NT_BI + NT_BJ) * NT_LD;
 
 struct GemmNT {
@@ -327,15 +327,15 @@ __global__ void __launch_bounds__(128) gemm_nt_3xtf32_kernel(GemmNT g) {
   float* C = g.C + (long long)z * g.c_z;
   const int i0 = blockIdx.y * NT_BI, j0 = blockIdx.x * NT_BJ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wi = warp * 16;                                    // 4 warps x 16 rows, all 32 columns
+  const int wi = warp * 32;                                    // 4 warps x 32 rows (2 m-tiles), all 32 columns
   const int gq = lane >> 2, tq = lane & 3;
-  float acc[4][4] = {};
+  float acc[2][4][4] = {};
 
   auto issue_stage = [&](int st, int k0) {
     float* As = nt_smem + st * NT_STAGE_FLOATS;
     float* Bs = As + NT_BI * NT_LD;
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {                              // A: 64 rows x 32 k = 512 float4
+    for (int h = 0; h < 8; ++h) {                              // A: 128 rows x 32 k = 1024 float4
       const int e = threadIdx.x + 128 * h;
       const int i = e >> 3, k = (e & 7) * 4;
       const bool ok = i0 + i < g.I && k0 + k < g.K;
@@ -366,44 +366,49 @@ __global__ void __launch_bounds__(128) gemm_nt_3xtf32_kernel(GemmNT g) {
     const float* Bs = As + NT_BI * NT_LD;
 #pragma unroll
     for (int kk = 0; kk < NT_BK; kk += 8) {
-      float af[4], bf[4][2];
-      af[0] = As[(wi + gq) * NT_LD + kk + tq];
-      af[1] = As[(wi + gq + 8) * NT_LD + kk + tq];
-      af[2] = As[(wi + gq) * NT_LD + kk + tq + 4];
-      af[3] = As[(wi + gq + 8) * NT_LD + kk + tq + 4];
-      uint32_t ab[4], as_[4];
+      uint32_t ab[2][4], as_[2][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { ab[e] = f2tf32(af[e]); as_[e] = f2tf32(af[e] - __uint_as_float(ab[e])); }
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r0 = wi + mi * 16 + gq;
+        const float af[4] = {As[r0 * NT_LD + kk + tq], As[(r0 + 8) * NT_LD + kk + tq], As[r0 * NT_LD + kk + tq + 4],
+                             As[(r0 + 8) * NT_LD + kk + tq + 4]};
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        bf[ni][0] = Bs[(ni * 8 + gq) * NT_LD + kk + tq];
-        bf[ni][1] = Bs[(ni * 8 + gq) * NT_LD + kk + tq + 4];
-        uint32_t bb[2], bs[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) { bb[e] = f2tf32(bf[ni][e]); bs[e] = f2tf32(bf[ni][e] - __uint_as_float(bb[e])); }
+        for (int e = 0; e < 4; ++e) { ab[mi][e] = f2tf32(af[e]); as_[mi][e] = f2tf32(af[e] - __uint_as_float(ab[mi][e])); }
+      }
 #define EP_MMA_TF32(ACC, AA, BB)                                                                                   \
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
                : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                             \
                : "r"(AA[0]), "r"(AA[1]), "r"(AA[2]), "r"(AA[3]), "r"(BB[0]), "r"(BB[1]))
-        EP_MMA_TF32(acc[ni], as_, bb);
-        EP_MMA_TF32(acc[ni], ab, bs);
-        EP_MMA_TF32(acc[ni], ab, bb);
-#undef EP_MMA_TF32
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const float bf[2] = {Bs[(ni * 8 + gq) * NT_LD + kk + tq], Bs[(ni * 8 + gq) * NT_LD + kk + tq + 4]};
+        uint32_t bb[2], bs[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { bb[e] = f2tf32(bf[e]); bs[e] = f2tf32(bf[e] - __uint_as_float(bb[e])); }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          EP_MMA_TF32(acc[mi][ni], as_[mi], bb);
+          EP_MMA_TF32(acc[mi][ni], ab[mi], bs);
+          EP_MMA_TF32(acc[mi][ni], ab[mi], bb);
+        }
       }
+#undef EP_MMA_TF32
     }
   }
   const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
 #pragma unroll
-  for (int ni = 0; ni < 4; ++ni)
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = i0 + wi + gq + h * 8;
-      const int j = j0 + ni * 8 + tq * 2;
-      if (i < g.I) {
-        if (j < g.J) C[(long long)i * g.ldc + j] = acc[ni][2 * h] + (bias ? bias[j] : 0.f);
-        if (j + 1 < g.J) C[(long long)i * g.ldc + j + 1] = acc[ni][2 * h + 1] + (bias ? bias[j + 1] : 0.f);
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = i0 + wi + mi * 16 + gq + h * 8;
+        const int j = j0 + ni * 8 + tq * 2;
+        if (i < g.I) {
+          if (j < g.J) C[(long long)i * g.ldc + j] = acc[mi][ni][2 * h] + (bias ? bias[j] : 0.f);
+          if (j + 1 < g.J) C[(long long)i * g.ldc + j + 1] = acc[mi][ni][2 * h + 1] + (bias ? bias[j + 1] : 0.f);
+        }
       }
-    }
 }
 
 int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias, int I, int J, int K, int Z,

@@ -98,8 +98,8 @@ int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w,
  *                 and leaves dP = g_out . v_w and delta = dP . P in the workspace;
  *   ep_bwd_pool : streams x once, recomputes A, writes d_cls_token.  Must follow ep_bwd_proj on the
  *                 same stream with the same workspace. */
-int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int B, int N, int D, int M, int d_out,
-                float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes, void* stream);
+int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int x_dtype, int B, int N, int D, int M,
+                int d_out, float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes, void* stream);
 int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M, int d_out,
                 const float* S, const float* rowmax, const float* rowsum, float* d_cls_token,
                 void* workspace, size_t workspace_bytes, void* stream);

@@ -27,14 +27,14 @@ for (B, N, D, M, d_out) in [(256, 5, 256, 8, 1), (130, 3, 128, 32, 1), (64, 4, 2
     ws = torch.empty(lib.ep_workspace_bytes(B, N, D, M, d_out), dtype=torch.uint8, device=dev)
     _lib.check(lib.ep_fwd(x.data_ptr(), 0, cls.data_ptr(), W.data_ptr(), None, D ** -0.5, B, N, D, M, d_out, out.data_ptr(), S.data_ptr(), rm.data_ptr(), rs.data_ptr(), P.data_ptr(), None, ws.data_ptr(), ws.numel(), s()), "ep_fwd")
     g = torch.randn(B, Dp, device=dev); dvw = torch.empty(Dp, D, device=dev)
-    _lib.check(lib.ep_bwd_proj(g.data_ptr(), P.data_ptr(), W.data_ptr(), B, N, D, M, d_out, dvw.data_ptr(), None, ws.data_ptr(), ws.numel(), s()), "bwd_proj")
+    _lib.check(lib.ep_bwd_proj(g.data_ptr(), P.data_ptr(), W.data_ptr(), 1, B, N, D, M, d_out, dvw.data_ptr(), None, ws.data_ptr(), ws.numel(), s()), "bwd_proj")
     torch.cuda.synchronize()
     Wm = W.double().reshape(M, c, D)
     ref_out = torch.einsum("mjc,bmc->bmj", Wm, P.double()).reshape(B, Dp)
     ref_dvw = torch.einsum("bmj,bmc->mjc", g.double().reshape(B, M, c), P.double()).reshape(Dp, D)
     # dP sits at the start of the pooling part of the workspace: find it via the known layout (w_r, g_r first)
     au = lambda v: (v + 255) // 256 * 256
-    off = au(3 * D * D * 4) + au(3 * B * D * 4)
+    off = au(3 * D * D * 4) + au(3 * B * D * 4)  # dP (fp32 path, x_dtype=1 -> general family)
     dP = ws[off: off + B * M * D * 4].view(torch.float32).reshape(B, M, D)
     ref_dP = torch.einsum("bmj,mjc->bmc", g.double().reshape(B, M, c), Wm)
     print((B, N, D, M, d_out), "out %.2e d_v_w %.2e dP %.2e" % (rel(out, ref_out), rel(dvw, ref_dvw), rel(dP, ref_dP)), flush=True)
