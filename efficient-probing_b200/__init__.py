@@ -12,7 +12,10 @@ from .probe_heads import build_probe_head, make_ep_head, POOLINGS               
 from .optim import LARS, adjust_learning_rate                                        # noqa: F401
 from .trainer import EPHeadTrainer                                                   # noqa: F401
 from .flatgrad import FlatGradLayout, shard_range, allreduce_sum_                    # noqa: F401
+from .token_cache import TokenShard, TokenStream, write_shard, load_reference_npz, epoch_order   # noqa: F401
+from .head_io import load_head, save_checkpoint, export_head, evaluate                # noqa: F401
 from . import _lib                                                                   # noqa: F401
 
 __all__ = ["EfficientProbing", "EPPoolFunction", "ep_attention", "build_probe_head", "make_ep_head", "POOLINGS",
-           "LARS", "adjust_learning_rate", "EPHeadTrainer"]
+           "LARS", "adjust_learning_rate", "EPHeadTrainer", "FlatGradLayout", "shard_range", "TokenShard", "TokenStream",
+           "write_shard", "load_reference_npz", "load_head", "save_checkpoint", "export_head", "evaluate"]

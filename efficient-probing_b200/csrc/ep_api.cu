@@ -48,7 +48,7 @@ extern "C" int ep_set_gemm_mode(int mode) {
   return 0;
 }
 extern "C" int ep_set_debug(int flags) { ep::g_debug = flags; return 0; }
-ep::TimingRecord ep::g_timings[32];
+ep::TimingRecord ep::g_timings[512];
 int ep::g_ntimings = 0;
 extern "C" int ep_timing_count(void) { return ep::g_ntimings; }
 extern "C" int ep_timing_get(int i, char* name, int name_len, float* us) {
@@ -73,7 +73,7 @@ struct Ws {                      // workspace layout
 bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !(ep::g_debug & 128); }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 int dp_nt(int D) { return std::min(128, (D + 31) / 32 * 32); }     // column tile of the fused dP GEMM
-int col_tiles(int D) { return (D + dp_nt(D) - 1) / dp_nt(D); }
+int col_tiles(int D) { return 2 * ((D + dp_nt(D) - 1) / dp_nt(D)); }   // delta partials: two per column tile
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
@@ -81,7 +81,7 @@ Ws carve(int B, int N, int D, int M) {
   w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
   w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
-  w.delta = off; off += align_up((size_t)32 * B * M * sizeof(float), 256);   // up to 32 column-tile partials
+  w.delta = off; off += align_up((size_t)64 * B * M * sizeof(float), 256);   // up to 64 delta partials
   w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
   w.sm100 = off; off += align_up(sm100_workspace_bytes(B, N, D, M), 256);
   w.total = off;
@@ -175,7 +175,7 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
       TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1};
       TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1};
       int fam_rc = 0;
-      if (use_sm100(x_dtype, B, N, D, M, &fam_rc) && col_tiles(D) <= 32) {
+      if (use_sm100(x_dtype, B, N, D, M, &fam_rc) && col_tiles(D) <= 64) {
         // tcgen05 pooling kernels follow: the GEMM epilogue emits what they consume -- dP as bf16 hi/lo operand
         // rows and delta = dP . P as per-column-tile partials -- and fp32 dP is never written
         void* sm = (char*)workspace + w.sm100;
@@ -231,7 +231,7 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
     const int c = D / d_out / M;
-    const bool fused = use_tc() && c % 4 == 0 && col_tiles(D) <= 32;      // what ep_bwd_proj did (same predicate)
+    const bool fused = use_tc() && c % 4 == 0 && col_tiles(D) <= 64;      // what ep_bwd_proj did (same predicate)
     return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, fused ? nullptr : dP, delta,
                           fused ? col_tiles(D) : 1, d_cls_token, (char*)workspace + w.sm100, s);
   }

@@ -70,7 +70,7 @@ __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpr
 extern int g_debug;
 // developer aid (ep_set_debug bit 5): CUDA-event time of every kernel of one call, printed to stderr
 struct TimingRecord { char name[24]; float us; };
-extern TimingRecord g_timings[32];
+extern TimingRecord g_timings[512];
 extern int g_ntimings;
 struct StageTimer {
   bool on; cudaStream_t s; cudaEvent_t ev[12]; const char* name[12]; int n = 0;
@@ -85,7 +85,7 @@ struct StageTimer {
     for (int i = 1; i < n; ++i) {
       float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
       if (g_debug & 256) fprintf(stderr, "[ep timing] %-18s %8.1f us\n", name[i], ms * 1e3f);
-      if (g_ntimings < 32) {
+      if (g_ntimings < 512) {
         snprintf(g_timings[g_ntimings].name, sizeof(g_timings[0].name), "%s", name[i]);
         g_timings[g_ntimings++].us = ms * 1e3f;
       }

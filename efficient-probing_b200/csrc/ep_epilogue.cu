@@ -5,36 +5,35 @@
 namespace ep {
 
 // ---------------- BatchNorm1d(affine=False, eps) -- probe_heads.py:109-110 ----------------
-// one CTA per 32 features, 32x32 threads: x = feature (coalesced), y strides the batch.
-__device__ __forceinline__ float block_colsum(float v, float (*red)[33]) {
+// one CTA per 8 features (a 32-byte sector per row), 8 x 128 threads: x = feature, y strides the batch.
+// F/8 CTAs instead of F/32 keep 128 SMs busy at F = 1024; a warp still reads whole sectors.
+constexpr int BN_F = 8, BN_Y = 128;
+__device__ __forceinline__ float block_colsum(float v, float (*red)[BN_F + 1]) {
   red[threadIdx.y][threadIdx.x] = v;
   __syncthreads();
-  if (threadIdx.y == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x];
-    red[0][threadIdx.x] = t;
+  for (int h = BN_Y / 2; h > 0; h >>= 1) {
+    if (threadIdx.y < h) red[threadIdx.y][threadIdx.x] += red[threadIdx.y + h][threadIdx.x];
+    __syncthreads();
   }
-  __syncthreads();
   const float r = red[0][threadIdx.x];
   __syncthreads();
   return r;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(BN_F * BN_Y)
 bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float momentum, int training,
               float* __restrict__ running_mean, float* __restrict__ running_var, long long* nbt,
               float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  __shared__ float red[32][33];
-  const int f = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float red[BN_Y][BN_F + 1];
+  const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
   float mean, invstd;
   if (training) {
     float s = 0.f;
-    if (ok) for (int b = threadIdx.y; b < B; b += 32) s += h[(size_t)b * F + f];
+    if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) s += h[(size_t)b * F + f];
     mean = block_colsum(s, red) / B;
     float v = 0.f;
-    if (ok) for (int b = threadIdx.y; b < B; b += 32) { const float d = h[(size_t)b * F + f] - mean; v = fmaf(d, d, v); }
+    if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) { const float d = h[(size_t)b * F + f] - mean; v = fmaf(d, d, v); }
     const float var = block_colsum(v, red) / B;                    // biased, used to normalise
     invstd = rsqrtf(var + eps);
     if (ok && threadIdx.y == 0) {
@@ -49,17 +48,17 @@ bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float moment
     mean = ok ? running_mean[f] : 0.f;
     invstd = ok ? 1.f / sqrtf(running_var[f] + eps) : 0.f;
   }
-  if (ok) for (int b = threadIdx.y; b < B; b += 32) y[(size_t)b * F + f] = (h[(size_t)b * F + f] - mean) * invstd;
+  if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) y[(size_t)b * F + f] = (h[(size_t)b * F + f] - mean) * invstd;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(BN_F * BN_Y)
 bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ invstd, int B, int F,
               float* __restrict__ dh) {
-  __shared__ float red[32][33];
-  const int f = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float red[BN_Y][BN_F + 1];
+  const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
   float s1 = 0.f, s2 = 0.f;
-  if (ok) for (int b = threadIdx.y; b < B; b += 32) {
+  if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) {
     const float g = dy[(size_t)b * F + f];
     s1 += g;
     s2 = fmaf(g, y[(size_t)b * F + f], s2);
@@ -68,7 +67,7 @@ bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const f
   const float m2 = block_colsum(s2, red) / B;
   if (ok) {
     const float is = invstd[f];
-    for (int b = threadIdx.y; b < B; b += 32)
+    for (int b = threadIdx.y; b < B; b += BN_Y)
       dh[(size_t)b * F + f] = is * (dy[(size_t)b * F + f] - m1 - y[(size_t)b * F + f] * m2);
   }
 }
@@ -183,7 +182,7 @@ extern "C" int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum
                          void* stream) {
   if (!h || !y || !running_mean || !running_var) return EP_ERR_NULL;
   if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
-  bn_fwd_kernel<<<(F + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(h, B, F, eps, momentum, training, running_mean,
+  bn_fwd_kernel<<<(F + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, (cudaStream_t)stream>>>(h, B, F, eps, momentum, training, running_mean,
                                                                          running_var, nbt, y, save_mean, save_invstd);
   EP_LAUNCH_CHECK();
   return 0;
@@ -192,7 +191,7 @@ extern "C" int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum
 extern "C" int ep_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, void* stream) {
   if (!dy || !y || !save_invstd || !dh) return EP_ERR_NULL;
   if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
-  bn_bwd_kernel<<<(F + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(dy, y, save_invstd, B, F, dh);
+  bn_bwd_kernel<<<(F + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, (cudaStream_t)stream>>>(dy, y, save_invstd, B, F, dh);
   EP_LAUNCH_CHECK();
   return 0;
 }

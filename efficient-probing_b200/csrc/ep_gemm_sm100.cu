@@ -60,7 +60,7 @@ __device__ __forceinline__ float to_tf32(float v) {
   return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTC g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -142,7 +142,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       umma_commit(done_bar);
     }
   } else if (warp >= 4) {
-    const int wq = warp - 4;
+    const int wq = (warp - 4) & 3, eh = (warp - 4) >> 2;        // lane quadrant, half of the 16-column units
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int row = i0 + wq * 32 + lane;
@@ -185,18 +185,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       };
       // the P loads of the next 16 columns are in flight while the current ones are converted
-      load_p(0, pv[0]);
-      for (int c0 = 0; c0 < g.NT; c0 += 32) {
-        load_p(c0 + 16, pv[1]);
+      load_p(16 * eh, pv[0]);
+      for (int c0 = 16 * eh; c0 < g.NT; c0 += 64) {
+        load_p(c0 + 32, pv[1]);
         emit(c0, pv[0]);
-        load_p(c0 + 32, pv[0]);
-        if (c0 + 16 < g.NT) emit(c0 + 16, pv[1]);
+        load_p(c0 + 64, pv[0]);
+        if (c0 + 32 < g.NT) emit(c0 + 32, pv[1]);
       }
-      if (row < g.I) g.delta_part[(size_t)blockIdx.x * g.I * g.Mq + (size_t)row * g.Mq + z] = dsum;
+      // two partials per column tile (one per epilogue warp group)
+      if (row < g.I) g.delta_part[((size_t)blockIdx.x * 2 + eh) * g.I * g.Mq + (size_t)row * g.Mq + z] = dsum;
     } else {
     const bool vec = g.c_col == 1 && (g.c_row % 4) == 0 && (g.c_z % 4) == 0 && (j0 % 4) == 0 &&
                      ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    for (int c0 = 0; c0 < g.NT; c0 += 16) {
+    for (int c0 = 16 * eh; c0 < g.NT; c0 += 32) {
       uint32_t r[16];
       tmem_ld16(acc + (uint32_t)c0, r);
       tmem_ld_wait();
@@ -285,7 +286,7 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, i
     attr_set = true;
   }
   dim3 grid((g.J + g.NT - 1) / g.NT, (g.I + 127) / 128, Z);
-  gemm_tf32_kernel<<<grid, 256, smem, s>>>(tm_a, tm_b, g);
+  gemm_tf32_kernel<<<grid, 384, smem, s>>>(tm_a, tm_b, g);
   EP_LAUNCH_CHECK();
   return 0;
 }
