@@ -72,6 +72,13 @@ struct Ws {                      // workspace layout
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
 bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !(ep::g_debug & 128); }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
+// column tile of the classifier GEMMs: the narrowest that still gives every SM a tile
+int lin_nt(int rows, int cols) {
+  const int rt = (rows + 127) / 128;
+  for (int nt = 128; nt >= 64; nt >>= 1)
+    if (rt * ((cols + nt - 1) / nt) >= kNumSMs / 2 || nt == 64) return nt;
+  return 64;
+}
 int dp_nt(int D) { return std::min(128, (D + 31) / 32 * 32); }     // column tile of the fused dP GEMM
 int col_tiles(int D) { return 2 * ((D + dp_nt(D) - 1) / dp_nt(D)); }   // delta partials: two per column tile
 Ws carve(int B, int N, int D, int M) {
@@ -295,12 +302,16 @@ extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int
   LinWs lw;
   if (use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw)) {
     int rc;                                                     // 3xTF32: y' = [big|small|big], W' = [big|big|small]
+    StageTimer tm(s);
     if ((rc = launch_split3(W, lw.w_r, K, F, F, 1, s))) return rc;
     if ((rc = launch_split3(y, lw.y_r, B, F, F, 0, s))) return rc;
+    tm.mark("lin split3 W,y");
     const unsigned long long F3 = 3ull * F;
     TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1};
     TcSide Bm{lw.w_r, F3, (unsigned long long)K, 1ull, F3, F3 * K, TC_KMAJOR, 0, 1};
-    return tc_gemm(A, Bm, B, K, 3 * F, 1, 128, logits, K, 1, 0, b, 0, 0, s);
+    rc = tc_gemm(A, Bm, B, K, 3 * F, 1, lin_nt(B, K), logits, K, 1, 0, b, 0, 0, s);
+    tm.mark("lin logits gemm");
+    return rc;
   }
   GemmDesc g{};
   g.A = y; g.B = W; g.C = logits; g.bias = b;
@@ -315,6 +326,7 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   if (B <= 0 || F <= 0 || K <= 0) return EP_ERR_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  StageTimer tm(s);
   LinWs lw;
   const bool tc = use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw);
   (void)0;
@@ -322,6 +334,7 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
     if (!y) return EP_ERR_NULL;
     if (tc) {                      // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: batch-major operands, "TN" kernel
       if ((rc = launch_gemm_tn(dlogits, y, dW, K, F, B, 1, K, F, F, 0, 0, 0, s))) return rc;
+      tm.mark("lin dW tn-gemm");
     } else {
       GemmDesc g{};
       g.A = dlogits; g.B = y; g.C = dW;
@@ -336,10 +349,12 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
     if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05, 3xTF32, transposed weight copy
       if ((rc = launch_split3(dlogits, lw.d_r, B, K, K, 0, s))) return rc;            // [b][3K]
       if ((rc = launch_split3_transpose(W, lw.w_t, K, F, 1, 0, 0, 1, s))) return rc;  // [f][3K]
+      tm.mark("lin split3 dl,Wt");
       const unsigned long long K3 = 3ull * K;
       TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1};
       TcSide Bm{lw.w_t, K3, (unsigned long long)F, 1ull, K3, K3 * F, TC_KMAJOR, 0, 1};
-      if ((rc = tc_gemm(A, Bm, B, F, 3 * K, 1, 128, dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
+      if ((rc = tc_gemm(A, Bm, B, F, 3 * K, 1, lin_nt(B, F), dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
+      tm.mark("lin dy gemm");
     } else {
       GemmDesc g{};
       g.A = dlogits; g.B = W; g.C = dy;

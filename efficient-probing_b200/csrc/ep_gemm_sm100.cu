@@ -22,7 +22,7 @@ constexpr int kGK = 32;                       // contraction elements per stage 
 constexpr int kGStages = 4;
 
 struct GemmTC {
-  int I, J, K;                                // C is I x J, contraction K
+  int I, J, K, Z;                             // C is I x J per batch entry z < Z, contraction K
   int NT;                                     // column tile (multiple of 32, <= 256)
   int a_mn, b_mn;                             // operand majors
   int a_swap, b_swap;                         // 0: coords (c0, row/k, z); 1: coords (c0, z, row/k)
@@ -62,6 +62,9 @@ __device__ __forceinline__ float to_tf32(float v) {
 
 __global__ void __launch_bounds__(384, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTC g) {
+  // persistent: each CTA walks output tiles (column tile fastest, then row tile, then batch); the smem ring
+  // runs on across tiles and the accumulator is double-buffered in TMEM, so the epilogue of one tile
+  // overlaps the loads and MMAs of the next and the per-CTA set-up cost is paid once
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -71,15 +74,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t bar_base = smem_base + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kGStages + s); };
-  const uint32_t done_bar = bar_base + 8u * (2 * kGStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kGStages + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (g.stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * g.stages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * g.stages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * g.stages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-  const uint32_t tmem_cols = g.NT <= 32 ? 32 : g.NT <= 64 ? 64 : g.NT <= 128 ? 128 : 256;
+  const uint32_t tmem_cols = g.NT <= 16 ? 32 : g.NT <= 32 ? 64 : g.NT <= 64 ? 128 : g.NT <= 128 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(done_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 256); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a); prefetch_tmap(&tm_b); }
@@ -88,143 +92,166 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int i0 = blockIdx.y * 128, j0 = blockIdx.x * g.NT, z = blockIdx.z;
   const int nk = (g.K + kGK - 1) / kGK;
-  const int za = z / g.a_zdiv, zb = z / g.b_zdiv;
+  const int n_ct = (g.J + g.NT - 1) / g.NT, n_rt = (g.I + 127) / 128;
+  const int ntiles = n_ct * n_rt * g.Z;
+  auto tile_coords = [&](int t, int& i0, int& j0, int& z) {
+    const int ct = t % n_ct, r = t / n_ct;
+    j0 = ct * g.NT; i0 = (r % n_rt) * 128; z = r / n_rt;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
-        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-        const int k0 = kc * kGK;
-        if (!g.a_mn) {                                         // [128 rows x 32 k]
-          tma_load_3d(dst, &tm_a, full_bar(s), k0, g.a_swap ? za : i0, g.a_swap ? i0 : za);
-        } else {                                               // 4 atoms of [32 k-rows x 32 mn]
-          for (int a = 0; a < 4; ++a)
-            tma_load_3d(dst + (uint32_t)a * 4096u, &tm_a, full_bar(s), i0 + 32 * a, g.a_swap ? za : k0,
-                        g.a_swap ? k0 : za);
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int i0, j0, z;
+        tile_coords(t, i0, j0, z);
+        const int za = z / g.a_zdiv, zb = z / g.b_zdiv;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          const int k0 = kc * kGK;
+          if (!g.a_mn) {                                       // [128 rows x 32 k]
+            tma_load_3d(dst, &tm_a, full_bar(s), k0, g.a_swap ? za : i0, g.a_swap ? i0 : za);
+          } else {                                             // 4 atoms of [32 k-rows x 32 mn]
+            for (int a = 0; a < 4; ++a)
+              tma_load_3d(dst + (uint32_t)a * 4096u, &tm_a, full_bar(s), i0 + 32 * a, g.a_swap ? za : k0,
+                          g.a_swap ? k0 : za);
+          }
+          const uint32_t bdst = dst + a_bytes;
+          if (!g.b_mn) {                                       // [NT rows x 32 k]
+            tma_load_3d(bdst, &tm_b, full_bar(s), k0, g.b_swap ? zb : j0, g.b_swap ? j0 : zb);
+          } else {
+            for (int a = 0; a < g.NT / 32; ++a)
+              tma_load_3d(bdst + (uint32_t)a * 4096u, &tm_b, full_bar(s), j0 + 32 * a, g.b_swap ? zb : k0,
+                          g.b_swap ? k0 : zb);
+          }
+          if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
-        const uint32_t bdst = dst + a_bytes;
-        if (!g.b_mn) {                                         // [NT rows x 32 k]
-          tma_load_3d(bdst, &tm_b, full_bar(s), k0, g.b_swap ? zb : j0, g.b_swap ? j0 : zb);
-        } else {
-          for (int a = 0; a < g.NT / 32; ++a)
-            tma_load_3d(bdst + (uint32_t)a * 4096u, &tm_b, full_bar(s), j0 + 32 * a, g.b_swap ? zb : k0,
-                        g.b_swap ? k0 : zb);
-        }
-        if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(128, g.NT, g.a_mn, g.b_mn);
-      int s = 0;
+      int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(full_bar(s), ph);
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t asm_ = smem_base + (uint32_t)s * stage_bytes, bsm = asm_ + a_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * g.NT);
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t asm_ = smem_base + (uint32_t)s * stage_bytes, bsm = asm_ + a_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                          // UMMA K = 8 fp32
-          const uint64_t ad = g.a_mn ? smem_desc_sw128(asm_ + 1024u * k, 4096, 1024)
-                                     : smem_desc_sw128(asm_ + 32u * k, 16, 1024);
-          const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + 1024u * k, 4096, 1024)
-                                     : smem_desc_sw128(bsm + 32u * k, 16, 1024);
-          umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+          for (int k = 0; k < 4; ++k) {                        // UMMA K = 8 fp32
+            const uint64_t ad = g.a_mn ? smem_desc_sw128(asm_ + 1024u * k, 4096, 1024)
+                                       : smem_desc_sw128(asm_ + 32u * k, 16, 1024);
+            const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + 1024u * k, 4096, 1024)
+                                       : smem_desc_sw128(bsm + 32u * k, 16, 1024);
+            umma_tf32(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+          }
+          umma_commit(empty_bar(s));
+          if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(empty_bar(s));
-        if (++s == g.stages) { s = 0; ph ^= 1u; }
+        umma_commit(tfull_bar(buf));
       }
-      umma_commit(done_bar);
     }
   } else if (warp >= 4) {
     const int wq = (warp - 4) & 3, eh = (warp - 4) >> 2;        // lane quadrant, half of the 16-column units
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-    const int row = i0 + wq * 32 + lane;
-    const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16);
-    float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
-    const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
-    if (g.epi_mode == 1) {
-      // row = sample b, z = query m, columns = d (J == D)
-      const float* prow = g.P + ((size_t)row * g.Mq + z) * g.J;
-      __nv_bfloat16* hrow = g.hl + ((size_t)row * g.Jrows + 2 * z) * g.J;
-      float dsum = 0.f;
-      const bool rok = row < g.I;
-      float4 pv[2][4];
-      auto load_p = [&](int c0, float4 (&dst)[4]) {
-        const int col = j0 + c0;
-        if (rok && c0 < g.NT && col + 16 <= g.J) {
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      int i0, j0, z;
+      tile_coords(t, i0, j0, z);
+      const int buf = it & 1;
+      mbar_wait(tfull_bar(buf), ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+      const int row = i0 + wq * 32 + lane;
+      const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * g.NT);
+      if (g.epi_mode == 1) {
+        // row = sample b, z = query m, columns = d (J == D)
+        const float* prow = g.P + ((size_t)row * g.Mq + z) * g.J;
+        __nv_bfloat16* hrow = g.hl + ((size_t)row * g.Jrows + 2 * z) * g.J;
+        float dsum = 0.f;
+        const bool rok = row < g.I;
+        float4 pv[2][4];
+        auto load_p = [&](int c0, float4 (&dst)[4]) {
+          const int col = j0 + c0;
+          if (rok && c0 < g.NT && col + 16 <= g.J) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(prow + col) + q);
-        }
-      };
-      auto emit = [&](int c0, const float4 (&src)[4]) {
-        uint32_t r[16];
-        tmem_ld16(acc + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int col = j0 + c0;
-        if (rok && col + 16 <= g.J) {
-          const float* pf = reinterpret_cast<const float*>(src);
-          __align__(16) __nv_bfloat16 hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float v = __uint_as_float(r[i]);
-            dsum = fmaf(v, pf[i], dsum);
-            hi[i] = __float2bfloat16_rn(v);
-            lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
+            for (int q = 0; q < 4; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(prow + col) + q);
           }
-          reinterpret_cast<uint4*>(hrow + col)[0] = reinterpret_cast<const uint4*>(hi)[0];
-          reinterpret_cast<uint4*>(hrow + col)[1] = reinterpret_cast<const uint4*>(hi)[1];
-          reinterpret_cast<uint4*>(hrow + g.J + col)[0] = reinterpret_cast<const uint4*>(lo)[0];
-          reinterpret_cast<uint4*>(hrow + g.J + col)[1] = reinterpret_cast<const uint4*>(lo)[1];
-        }
-      };
-      // the P loads of the next 16 columns are in flight while the current ones are converted
-      load_p(16 * eh, pv[0]);
-      for (int c0 = 16 * eh; c0 < g.NT; c0 += 64) {
-        load_p(c0 + 32, pv[1]);
-        emit(c0, pv[0]);
-        load_p(c0 + 64, pv[0]);
-        if (c0 + 32 < g.NT) emit(c0 + 32, pv[1]);
-      }
-      // two partials per column tile (one per epilogue warp group)
-      if (row < g.I) g.delta_part[((size_t)blockIdx.x * 2 + eh) * g.I * g.Mq + (size_t)row * g.Mq + z] = dsum;
-    } else {
-    const bool vec = g.c_col == 1 && (g.c_row % 4) == 0 && (g.c_z % 4) == 0 && (j0 % 4) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    for (int c0 = 16 * eh; c0 < g.NT; c0 += 32) {
-      uint32_t r[16];
-      tmem_ld16(acc + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (row < g.I) {
-        if (vec && j0 + c0 + 16 <= g.J) {                      // 64 contiguous bytes per lane
-          float v[16];
+        };
+        auto emit = [&](int c0, const float4 (&src)[4]) {
+          uint32_t r[16];
+          tmem_ld16(acc + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int col = j0 + c0;
+          if (rok && col + 16 <= g.J) {
+            const float* pf = reinterpret_cast<const float*>(src);
+            __align__(16) __nv_bfloat16 hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + j0 + c0 + i) : 0.f);
-            if (g.round_tf32) v[i] = to_tf32(v[i]);
+            for (int i = 0; i < 16; ++i) {
+              const float v = __uint_as_float(r[i]);
+              dsum = fmaf(v, pf[i], dsum);
+              hi[i] = __float2bfloat16_rn(v);
+              lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
+            }
+            reinterpret_cast<uint4*>(hrow + col)[0] = reinterpret_cast<const uint4*>(hi)[0];
+            reinterpret_cast<uint4*>(hrow + col)[1] = reinterpret_cast<const uint4*>(hi)[1];
+            reinterpret_cast<uint4*>(hrow + g.J + col)[0] = reinterpret_cast<const uint4*>(lo)[0];
+            reinterpret_cast<uint4*>(hrow + g.J + col)[1] = reinterpret_cast<const uint4*>(lo)[1];
           }
+        };
+        // the P loads of the next 16 columns are in flight while the current ones are converted
+        load_p(16 * eh, pv[0]);
+        for (int c0 = 16 * eh; c0 < g.NT; c0 += 64) {
+          load_p(c0 + 32, pv[1]);
+          emit(c0, pv[0]);
+          load_p(c0 + 64, pv[0]);
+          if (c0 + 32 < g.NT) emit(c0 + 32, pv[1]);
+        }
+        // two partials per column tile (one per epilogue warp group)
+        if (rok) g.delta_part[((size_t)(j0 / g.NT) * 2 + eh) * g.I * g.Mq + (size_t)row * g.Mq + z] = dsum;
+      } else {
+        float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
+        const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
+        const bool vec = g.c_col == 1 && (g.c_row % 4) == 0 && (g.c_z % 4) == 0 && (j0 % 4) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+        for (int c0 = 16 * eh; c0 < g.NT; c0 += 32) {
+          uint32_t r[16];
+          tmem_ld16(acc + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (row < g.I) {
+            if (vec && j0 + c0 + 16 <= g.J) {                  // 64 contiguous bytes per lane
+              float v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(crow + j0 + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
+              for (int i = 0; i < 16; ++i) {
+                v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + j0 + c0 + i) : 0.f);
+                if (g.round_tf32) v[i] = to_tf32(v[i]);
+              }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = j0 + c0 + i;
-            if (col < g.J) {
-              float v = __uint_as_float(r[i]) + (bias ? __ldg(bias + col) : 0.f);
-              if (g.round_tf32) v = to_tf32(v);
-              crow[(long long)col * g.c_col] = v;
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(crow + j0 + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int col = j0 + c0 + i;
+                if (col < g.J) {
+                  float v = __uint_as_float(r[i]) + (bias ? __ldg(bias + col) : 0.f);
+                  if (g.round_tf32) v = to_tf32(v);
+                  crow[(long long)col * g.c_col] = v;
+                }
+              }
             }
           }
         }
       }
-    }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
     }
   }
   tc_fence_before();
@@ -278,15 +305,16 @@ bool gemm_tc_available() { return encode_fn() != nullptr; }
 int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s);
 
 int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s) {
-  g.stages = std::max(1, std::min(kGStages, (g.K + kGK - 1) / kGK));
+  g.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (190 * 1024) / (128 * 128 + (size_t)g.NT * 128)));
   const size_t smem = (size_t)g.stages * (128 * 128 + (size_t)g.NT * 128) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  dim3 grid((g.J + g.NT - 1) / g.NT, (g.I + 127) / 128, Z);
-  gemm_tf32_kernel<<<grid, 384, smem, s>>>(tm_a, tm_b, g);
+  g.Z = Z;
+  const int ntiles = ((g.J + g.NT - 1) / g.NT) * ((g.I + 127) / 128) * Z;
+  gemm_tf32_kernel<<<std::min(ntiles, kNumSMs), 384, smem, s>>>(tm_a, tm_b, g);
   EP_LAUNCH_CHECK();
   return 0;
 }
