@@ -70,6 +70,9 @@ struct Ws {                      // workspace layout
 };
 // The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
+// 3-term operand copies of the K-concatenated GEMMs: bf16 hi/lo (kind::f16, half the bytes, twice the MMA
+// rate) rather than tf32 big/small; both give ~1e-5.  bf16 rows need K % 8 == 0 for 16-byte TMA strides.
+constexpr int kSplitBf16 = 1;
 bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !(ep::g_debug & 128); }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 // column tile of the classifier GEMMs: the narrowest that still gives every SM a tile
@@ -175,12 +178,13 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
     {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05, 3xTF32 (dP drives the query gradient)
       float* g3 = (float*)((char*)workspace + w.g_r);              // [(b, m)][3c]  = [big | small | big]
       float* w3 = (float*)((char*)workspace + w.w_t);              // [m][d][3c]    = [big | big | small]
-      if ((rc = launch_split3(g_out, g3, (long long)B * M, c, c, 0, s))) return rc;
-      if ((rc = launch_split3_transpose(v_w, w3, c, D, M, (long long)c * D, (long long)3 * c * D, 1, s))) return rc;
+      const int bf = kSplitBf16 && c % 8 == 0;               // bf16 rows need 16-byte strides: 3c * 2 B
+      if ((rc = launch_split3(g_out, g3, (long long)B * M, c, c, 0, bf, s))) return rc;
+      if ((rc = launch_split3_transpose(v_w, w3, c, D, M, (long long)c * D, (long long)3 * c * D, 1, bf, s))) return rc;
       tm.mark("split3 g, W");
       const unsigned long long c3 = 3ull * c;
-      TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1};
-      TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1};
+      TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1, bf};
+      TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1, bf};
       int fam_rc = 0;
       if (use_sm100(x_dtype, B, N, D, M, &fam_rc) && col_tiles(D) <= 64) {
         // tcgen05 pooling kernels follow: the GEMM epilogue emits what they consume -- dP as bf16 hi/lo operand
@@ -303,12 +307,13 @@ extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int
   if (use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw)) {
     int rc;                                                     // 3xTF32: y' = [big|small|big], W' = [big|big|small]
     StageTimer tm(s);
-    if ((rc = launch_split3(W, lw.w_r, K, F, F, 1, s))) return rc;
-    if ((rc = launch_split3(y, lw.y_r, B, F, F, 0, s))) return rc;
+    const int bf = kSplitBf16 && F % 8 == 0;
+    if ((rc = launch_split3(W, lw.w_r, K, F, F, 1, bf, s))) return rc;
+    if ((rc = launch_split3(y, lw.y_r, B, F, F, 0, bf, s))) return rc;
     tm.mark("lin split3 W,y");
     const unsigned long long F3 = 3ull * F;
-    TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1};
-    TcSide Bm{lw.w_r, F3, (unsigned long long)K, 1ull, F3, F3 * K, TC_KMAJOR, 0, 1};
+    TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1, bf};
+    TcSide Bm{lw.w_r, F3, (unsigned long long)K, 1ull, F3, F3 * K, TC_KMAJOR, 0, 1, bf};
     rc = tc_gemm(A, Bm, B, K, 3 * F, 1, lin_nt(B, K), logits, K, 1, 0, b, 0, 0, s);
     tm.mark("lin logits gemm");
     return rc;
@@ -347,12 +352,13 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   if (dy) {
     if (!W) return EP_ERR_NULL;
     if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05, 3xTF32, transposed weight copy
-      if ((rc = launch_split3(dlogits, lw.d_r, B, K, K, 0, s))) return rc;            // [b][3K]
-      if ((rc = launch_split3_transpose(W, lw.w_t, K, F, 1, 0, 0, 1, s))) return rc;  // [f][3K]
+      const int bf = kSplitBf16 && K % 8 == 0;
+      if ((rc = launch_split3(dlogits, lw.d_r, B, K, K, 0, bf, s))) return rc;            // [b][3K]
+      if ((rc = launch_split3_transpose(W, lw.w_t, K, F, 1, 0, 0, 1, bf, s))) return rc;  // [f][3K]
       tm.mark("lin split3 dl,Wt");
       const unsigned long long K3 = 3ull * K;
-      TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1};
-      TcSide Bm{lw.w_t, K3, (unsigned long long)F, 1ull, K3, K3 * F, TC_KMAJOR, 0, 1};
+      TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1, bf};
+      TcSide Bm{lw.w_t, K3, (unsigned long long)F, 1ull, K3, K3 * F, TC_KMAJOR, 0, 1, bf};
       if ((rc = tc_gemm(A, Bm, B, F, 3 * K, 1, lin_nt(B, F), dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
       tm.mark("lin dy gemm");
     } else {

@@ -111,11 +111,12 @@ int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s);
 // C[z][i][j] = sum_k A.. B..; see ep_api.cu for the operand descriptions
 enum TcOperand { TC_KMAJOR = 0, TC_MNMAJOR = 1 };
 struct TcSide {            // one operand as a 3-D fp32 tensor (d0 contiguous) and how tiles index it
-  const float* base;
+  const void* base;
   unsigned long long d0, d1, d2, s1, s2;   // sizes and element strides of dims 1, 2
   int mn_major;            // 0: d0 is the contraction index; 1: d0 is the output (row/col) index
   int swap;                // 0: dim1 = rows-or-k, dim2 = batch; 1: dim1 = batch, dim2 = rows-or-k
   int zdiv;                // batch coordinate = z / zdiv
+  int bf16;                // elements are bf16 (both operands of a GEMM must agree); 0 = fp32 read as tf32
 };
 int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,
             long long c_col, long long c_z, const float* bias, long long bias_z, int round_out, cudaStream_t s);
@@ -123,9 +124,10 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
 int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K, int Z, long long lda, long long ldb,
                    long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s);
 bool gemm_tn_ok(int I, int J, long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z);
-int launch_split3(const float* src, float* dst, long long R, int K, long long ld, int kind, cudaStream_t s);
-int launch_split3_transpose(const float* src, float* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
-                            cudaStream_t s);
+// 3-term split copies for the tcgen05 GEMMs; bf16 != 0: dst is bf16 (hi/lo split), else fp32 (tf32 big/small)
+int launch_split3(const float* src, void* dst, long long R, int K, long long ld, int kind, int bf16, cudaStream_t s);
+int launch_split3_transpose(const float* src, void* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
+                            int bf16, cudaStream_t s);
 int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias, int I, int J, int K, int Z,
                     long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z,
                     long long bias_z, cudaStream_t s);

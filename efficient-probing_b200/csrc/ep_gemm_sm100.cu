@@ -18,7 +18,7 @@
 namespace ep {
 using namespace ptx;
 
-constexpr int kGK = 32;                       // contraction elements per stage (one 128-byte swizzle row of fp32)
+constexpr int kGK = 32;                       // contraction elements per stage: one 128-byte swizzle row (32 fp32 / 64 bf16)
 constexpr int kGStages = 4;
 
 struct GemmTC {
@@ -30,7 +30,8 @@ struct GemmTC {
   float* C; const float* bias;
   long long c_row, c_col, c_z, bias_z;        // element strides of C and bias
   int round_tf32;                             // round the stored result to tf32 (it feeds another TF32 GEMM)
-  int stages;                                 // smem ring depth (<= kGStages; short contractions use fewer)
+  int stages;                                 // smem ring depth
+  int bf16;                                   // operands are bf16 (kind::f16, 64 elements per stage) instead of fp32/tf32
   // epilogue mode 1 (projection backward, C = dP[b, z=m, d]): instead of storing fp32 dP, write it as the
   // bf16 hi/lo operand rows (B, Jrows, D) the dA kernel consumes and the partial delta = sum_d dP * P of this
   // column tile -- dP never touches memory in fp32
@@ -51,6 +52,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -92,7 +102,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int nk = (g.K + kGK - 1) / kGK;
+  const int gk = g.bf16 ? 2 * kGK : kGK;                      // elements per 128-byte row
+  const int nk = (g.K + gk - 1) / gk;
   const int n_ct = (g.J + g.NT - 1) / g.NT, n_rt = (g.I + 127) / 128;
   const int ntiles = n_ct * n_rt * g.Z;
   auto tile_coords = [&](int t, int& i0, int& j0, int& z) {
@@ -112,8 +123,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-          const int k0 = kc * kGK;
-          if (!g.a_mn) {                                       // [128 rows x 32 k]
+          const int k0 = kc * gk;
+          if (!g.a_mn) {                                       // [128 rows x one 128-byte row of k]
             tma_load_3d(dst, &tm_a, full_bar(s), k0, g.a_swap ? za : i0, g.a_swap ? i0 : za);
           } else {                                             // 4 atoms of [32 k-rows x 32 mn]
             for (int a = 0; a < 4; ++a)
@@ -134,7 +145,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(128, g.NT, g.a_mn, g.b_mn);
+      const uint32_t idesc = g.bf16 ? idesc_bf16(128, g.NT, g.a_mn, g.b_mn) : idesc_tf32(128, g.NT, g.a_mn, g.b_mn);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -152,7 +163,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                        : smem_desc_sw128(asm_ + 32u * k, 16, 1024);
             const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + 1024u * k, 4096, 1024)
                                        : smem_desc_sw128(bsm + 32u * k, 16, 1024);
-            umma_tf32(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+            if (g.bf16) umma_bf16(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+            else umma_tf32(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
           }
           umma_commit(empty_bar(s));
           if (++s == g.stages) { s = 0; ph ^= 1u; }
@@ -286,16 +298,18 @@ EncodeTiledFn encode_fn() {
 }
 }  // namespace
 
-// fp32 tensor (d2, d1, d0) with element strides (s2, s1, 1); box (b2, b1, 32)
+// fp32 / bf16 tensor (d2, d1, d0) with element strides (s2, s1, 1); box (b2, b1, one 128-byte row)
 int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
-                  uint32_t b1, uint32_t b2) {
+                  uint32_t b1, uint32_t b2, int bf16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return EP_ERR_DEVICE;
+  const uint64_t es = bf16 ? 2 : 4;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {s1 * 4, s2 * 4};
-  cuuint32_t box[3] = {32, b1, b2};
+  cuuint64_t strides[2] = {s1 * es, s2 * es};
+  cuuint32_t box[3] = {bf16 ? 64u : 32u, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                  const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : EP_ERR_UNSUPPORTED;
@@ -322,7 +336,7 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, i
 static int side_tmap(CUtensorMap* m, const TcSide& sd, int tile_rows) {
   // K-major: box = 32 k x tile_rows rows; MN-major: box = 32 mn x 32 k-rows
   const uint32_t r = sd.mn_major ? 32u : (uint32_t)tile_rows;
-  return make_tmap_f32(m, sd.base, sd.d0, sd.d1, sd.d2, sd.s1, sd.s2, sd.swap ? 1u : r, sd.swap ? r : 1u);
+  return make_tmap_f32(m, sd.base, sd.d0, sd.d1, sd.d2, sd.s1, sd.s2, sd.swap ? 1u : r, sd.swap ? r : 1u, sd.bf16);
 }
 
 int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, const float* P, void* hl,
@@ -336,6 +350,7 @@ int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int
   g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
   g.epi_mode = 1; g.P = P; g.hl = (__nv_bfloat16*)hl; g.delta_part = delta_part; g.Mq = Z; g.Jrows = Jrows;
+  g.bf16 = A.bf16;
   return launch_gemm_tc(ta, tb, g, Z, s);
 }
 
@@ -351,6 +366,7 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
   g.C = C; g.bias = bias; g.c_row = c_row; g.c_col = c_col; g.c_z = c_z; g.bias_z = bias_z;
   g.round_tf32 = round_out;
+  g.bf16 = A.bf16;
   return launch_gemm_tc(ta, tb, g, Z, s);
 }
 

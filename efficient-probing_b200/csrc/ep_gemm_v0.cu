@@ -3,6 +3,8 @@
 // tensor-core kernels replace it where the layout allows.
 #include "ep_common.cuh"
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 namespace ep {
@@ -256,37 +258,52 @@ int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K
 // the product is accurate to ~1e-6 instead of TF32's 3e-4.
 //   kind 0: A-type, kind 1: B-type.  transpose: dst rows are src columns (weights read MN-major).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split3_store(float* drow, int K, int k, float x, int kind) {
-  const float big = round_tf32(x);
-  const float small = round_tf32(x - big);
+template <typename T> struct Split3;
+template <> struct Split3<float> {                      // tf32 big / small
+  __device__ static void split(float x, float& big, float& small) { big = round_tf32(x); small = round_tf32(x - big); }
+};
+template <> struct Split3<__nv_bfloat16> {              // bf16 hi / lo
+  __device__ static void split(float x, __nv_bfloat16& big, __nv_bfloat16& small) {
+    big = __float2bfloat16_rn(x);
+    small = __float2bfloat16_rn(x - __bfloat162float(big));
+  }
+};
+template <typename T>
+__device__ __forceinline__ void split3_store(T* drow, int K, int k, float x, int kind) {
+  T big, small;
+  Split3<T>::split(x, big, small);
   drow[k] = big;
   drow[K + k] = kind == 0 ? small : big;
   drow[2 * K + k] = kind == 0 ? big : small;
 }
 
 // src [R x K] (row stride ld) -> dst [R x 3K]
-__global__ void split3_kernel(const float* __restrict__ src, float* __restrict__ dst, long long R, int K, long long ld,
+template <typename T>
+__global__ void split3_kernel(const float* __restrict__ src, T* __restrict__ dst, long long R, int K, long long ld,
                               int kind) {
   const long long total = R * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / K;
     const int k = (int)(i - r * K);
-    split3_store(dst + r * 3 * K, K, k, __ldg(src + r * ld + k), kind);
+    split3_store<T>(dst + r * 3 * K, K, k, __ldg(src + r * ld + k), kind);
   }
 }
-int launch_split3(const float* src, float* dst, long long R, int K, long long ld, int kind, cudaStream_t s) {
+int launch_split3(const float* src, void* dst, long long R, int K, long long ld, int kind, int bf16, cudaStream_t s) {
   const long long total = R * K;
-  split3_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 8 * kNumSMs), 256, 0, s>>>(src, dst, R, K, ld, kind);
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 8 * kNumSMs);
+  if (bf16) split3_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, (__nv_bfloat16*)dst, R, K, ld, kind);
+  else split3_kernel<float><<<grid, 256, 0, s>>>(src, (float*)dst, R, K, ld, kind);
   EP_LAUNCH_CHECK();
   return 0;
 }
 
 // src[z] is [K x R] (K rows, row stride R); dst[z] is [R x 3K]  (the transposed, K-major copy)
-__global__ void split3_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int R,
+template <typename T>
+__global__ void split3_transpose_kernel(const float* __restrict__ src, T* __restrict__ dst, int K, int R,
                                         long long src_z, long long dst_z, int kind) {
   __shared__ float tile[32][33];
   const float* sp = src + (long long)blockIdx.z * src_z;
-  float* dp = dst + (long long)blockIdx.z * dst_z;
+  T* dp = dst + (long long)blockIdx.z * dst_z;
   const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int k = k0 + i, r = r0 + threadIdx.x;
@@ -295,12 +312,14 @@ __global__ void split3_transpose_kernel(const float* __restrict__ src, float* __
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, k = k0 + threadIdx.x;
-    if (r < R && k < K) split3_store(dp + (long long)r * 3 * K, K, k, tile[threadIdx.x][i], kind);
+    if (r < R && k < K) split3_store<T>(dp + (long long)r * 3 * K, K, k, tile[threadIdx.x][i], kind);
   }
 }
-int launch_split3_transpose(const float* src, float* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
-                            cudaStream_t s) {
-  split3_transpose_kernel<<<dim3((R + 31) / 32, (K + 31) / 32, Z), dim3(32, 8), 0, s>>>(src, dst, K, R, src_z, dst_z, kind);
+int launch_split3_transpose(const float* src, void* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
+                            int bf16, cudaStream_t s) {
+  const dim3 grid((R + 31) / 32, (K + 31) / 32, Z), blk(32, 8);
+  if (bf16) split3_transpose_kernel<__nv_bfloat16><<<grid, blk, 0, s>>>(src, (__nv_bfloat16*)dst, K, R, src_z, dst_z, kind);
+  else split3_transpose_kernel<float><<<grid, blk, 0, s>>>(src, (float*)dst, K, R, src_z, dst_z, kind);
   EP_LAUNCH_CHECK();
   return 0;
 }
