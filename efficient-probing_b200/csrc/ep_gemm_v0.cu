@@ -125,7 +125,7 @@ int launch_rowdot(const float* a, const float* b, long long rows, int cols, floa
 // ------------------------------------------------------------------------------------------------
 namespace ep {
 
-constexpr int TN_BI = 64, TN_BJ = 128, TN_BK = 16, TN_LDA = TN_BI + 8, TN_LDB = TN_BJ + 8, TN_STAGES = 4;
+constexpr int TN_BI = 64, TN_BJ = 128, TN_BK = 32, TN_LDA = TN_BI + 8, TN_LDB = TN_BJ + 8, TN_STAGES = 4;
 constexpr int TN_STAGE_FLOATS = TN_BK * (TN_LDA + TN_LDB);
 
 __device__ __forceinline__ uint32_t f2tf32(float v) {
@@ -161,13 +161,14 @@ __global__ void __launch_bounds__(256) gemm_tn_mma_kernel(GemmTN g) {
   auto issue_stage = [&](int st, int k0) {
     float* As = tn_smem + st * TN_STAGE_FLOATS;
     float* Bs = As + TN_BK * TN_LDA;
-    {  // A chunk: 16 k x 64 i = 256 float4, one per thread
-      const int k = threadIdx.x >> 4, i = (threadIdx.x & 15) * 4;
+#pragma unroll
+    for (int h = 0; h < TN_BK / 16; ++h) {  // A chunk: BK k x 64 i, 16 k-rows per pass
+      const int k = (threadIdx.x >> 4) + 16 * h, i = (threadIdx.x & 15) * 4;
       const bool ok = k0 + k < g.K && i0 + i < g.I;
       cp_async16(As + k * TN_LDA + i, ok ? A + (long long)(k0 + k) * g.lda + i0 + i : A, ok ? 16 : 0);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {  // B chunk: 16 k x 128 j = 512 float4, two per thread
+    for (int h = 0; h < TN_BK / 8; ++h) {  // B chunk: BK k x 128 j, 8 k-rows per pass
       const int e = threadIdx.x + 256 * h;
       const int k = e >> 5, j = (e & 31) * 4;
       const bool ok = k0 + k < g.K && j0 + j < g.J;
@@ -398,19 +399,26 @@ __global__ void __launch_bounds__(128) gemm_nt_3xtf32_kernel(GemmNT g) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
                : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                             \
                : "r"(AA[0]), "r"(AA[1]), "r"(AA[2]), "r"(AA[3]), "r"(BB[0]), "r"(BB[1]))
+      uint32_t bb[4][2], bs[4][2];
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const float bf[2] = {Bs[(ni * 8 + gq) * NT_LD + kk + tq], Bs[(ni * 8 + gq) * NT_LD + kk + tq + 4]};
-        uint32_t bb[2], bs[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) { bb[e] = f2tf32(bf[e]); bs[e] = f2tf32(bf[e] - __uint_as_float(bb[e])); }
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi) {
-          EP_MMA_TF32(acc[mi][ni], as_[mi], bb);
-          EP_MMA_TF32(acc[mi][ni], ab[mi], bs);
-          EP_MMA_TF32(acc[mi][ni], ab[mi], bb);
-        }
+        for (int e = 0; e < 2; ++e) { bb[ni][e] = f2tf32(bf[e]); bs[ni][e] = f2tf32(bf[e] - __uint_as_float(bb[ni][e])); }
       }
+      // the three products are issued product-major so that back-to-back MMAs hit different accumulators
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) EP_MMA_TF32(acc[mi][ni], as_[mi], bb[ni]);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) EP_MMA_TF32(acc[mi][ni], ab[mi], bs[ni]);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) EP_MMA_TF32(acc[mi][ni], ab[mi], bb[ni]);
 #undef EP_MMA_TF32
     }
   }
