@@ -321,11 +321,7 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, i
 int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s) {
   g.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (190 * 1024) / (128 * 128 + (size_t)g.NT * 128)));
   const size_t smem = (size_t)g.stages * (128 * 128 + (size_t)g.NT * 128) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g.Z = Z;
   const int ntiles = ((g.J + g.NT - 1) / g.NT) * ((g.I + 127) / 128) * Z;
   gemm_tf32_kernel<<<std::min(ntiles, kNumSMs), 384, smem, s>>>(tm_a, tm_b, g);

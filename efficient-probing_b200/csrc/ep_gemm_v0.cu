@@ -71,24 +71,24 @@ int launch_gemm_v0(const GemmDesc& g, cudaStream_t s) {
   return 0;
 }
 
-// out[j] = sum_i a[i][j]   (bias gradients)
-__global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int j = blockIdx.x * 32 + threadIdx.x;
+// out[j] = sum_i a[i][j]   (bias gradients): 8 columns (one 32-byte sector per row) per CTA, 128 row-threads
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ a, int rows, int cols,
+                                                      float* __restrict__ out) {
+  __shared__ float red[128][9];
+  const int j = blockIdx.x * 8 + threadIdx.x;
   float s = 0.f;
   if (j < cols)
-    for (int i = threadIdx.y; i < rows; i += 8) s += a[(size_t)i * cols + j];
+    for (int i = threadIdx.y; i < rows; i += 128) s += a[(size_t)i * cols + j];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.y == 0 && j < cols) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-    out[j] = t;
+  for (int h = 64; h > 0; h >>= 1) {
+    if (threadIdx.y < h) red[threadIdx.y][threadIdx.x] += red[threadIdx.y + h][threadIdx.x];
+    __syncthreads();
   }
+  if (threadIdx.y == 0 && j < cols) out[j] = red[0][threadIdx.x];
 }
 int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s) {
-  colsum_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, s>>>(a, rows, cols, out);
+  colsum_kernel<<<(cols + 7) / 8, dim3(8, 128), 0, s>>>(a, rows, cols, out);
   EP_LAUNCH_CHECK();
   return 0;
 }
@@ -240,11 +240,7 @@ int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K
   if (!gemm_tn_ok(I, J, lda, ldb, ldc, a_z, b_z, c_z)) return EP_ERR_ALIGN;
   GemmTN g{A, B, C, I, J, K, lda, ldb, ldc, a_z, b_z, c_z};
   const int smem = TN_STAGES * TN_STAGE_FLOATS * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    EP_CUDA(cudaFuncSetAttribute(gemm_tn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  EP_CUDA(cudaFuncSetAttribute(gemm_tn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((J + TN_BJ - 1) / TN_BJ, (I + TN_BI - 1) / TN_BI, Z);
   gemm_tn_mma_kernel<<<grid, 256, smem, s>>>(g);
   EP_LAUNCH_CHECK();
@@ -445,11 +441,7 @@ int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias,
   if (((lda | ldb | a_z | b_z) & 3) || (K & 3)) return EP_ERR_ALIGN;
   GemmNT g{A, B, C, bias, I, J, K, lda, ldb, ldc, a_z, b_z, c_z, bias_z};
   const int smem = NT_STAGES * NT_STAGE_FLOATS * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    EP_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  EP_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((J + NT_BJ - 1) / NT_BJ, (I + NT_BI - 1) / NT_BI, Z);
   gemm_nt_3xtf32_kernel<<<grid, 128, smem, s>>>(g);
   EP_LAUNCH_CHECK();
