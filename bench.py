@@ -248,13 +248,13 @@ def main():
     hx = [pool_x[i].cpu().pin_memory() for i in range(2)]
     hy = [pool_y[i].cpu().pin_memory() for i in range(2)]
     for i in range(3):
-        tr.train_step_host(hx[i % 2], hy[i % 2])
+        tr.train_step_host(hx[i % 2], hy[i % 2], next_x_host=hx[(i + 1) % 2], next_targets_host=hy[(i + 1) % 2])
     barrier()
     e2e_steps = args.steps
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(e2e_steps):
-        tr.train_step_host(hx[i % 2], hy[i % 2])
+    for i in range(e2e_steps):               # step i+1's H2D copy is issued while step i computes
+        tr.train_step_host(hx[i % 2], hy[i % 2], next_x_host=hx[(i + 1) % 2], next_targets_host=hy[(i + 1) % 2])
     f1.record()
     barrier()
     ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)

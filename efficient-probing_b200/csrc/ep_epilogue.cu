@@ -129,7 +129,8 @@ struct LarsArgs {
 };
 // hyper = {lr, weight_decay, momentum, trust_coefficient, grad_scale}
 
-__global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float* __restrict__ hyper, float* norms) {
+// deterministic norms: every CTA writes its partial sums, the update kernel adds them in a fixed order
+__global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float* __restrict__ hyper, float* partial) {
   const int t = blockIdx.y;
   if (!a.trust[t]) return;
   const float wd = hyper[1], gs = hyper[4];
@@ -148,21 +149,33 @@ __global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float*
     float x = 0.f, y = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { x += r0[w]; y += r1[w]; }
-    atomicAdd(norms + 2 * t, x);
-    atomicAdd(norms + 2 * t + 1, y);
+    partial[((size_t)t * gridDim.x + blockIdx.x) * 2] = x;
+    partial[((size_t)t * gridDim.x + blockIdx.x) * 2 + 1] = y;
   }
 }
 
 __global__ void __launch_bounds__(256) lars_update_kernel(LarsArgs a, const float* __restrict__ hyper,
-                                                          const float* __restrict__ norms) {
+                                                          const float* __restrict__ partial) {
   const int t = blockIdx.y;
   const float lr = hyper[0], wd = hyper[1], mom = hyper[2], tc = hyper[3], gs = hyper[4];
-  float q = 1.f;
+  __shared__ float qs;
   const bool tr = a.trust[t] != 0;
-  if (tr) {
-    const float pn = sqrtf(norms[2 * t]), un = sqrtf(norms[2 * t + 1]);
-    q = (pn > 0.f && un > 0.f) ? tc * pn / un : 1.f;
+  if (threadIdx.x < 32) {
+    float q = 1.f;
+    if (tr) {
+      float x = 0.f, y = 0.f;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {       // fixed order: lane-strided, then butterfly
+        x += partial[((size_t)t * gridDim.x + i) * 2];
+        y += partial[((size_t)t * gridDim.x + i) * 2 + 1];
+      }
+      x = warp_sum(x); y = warp_sum(y);
+      const float pn = sqrtf(x), un = sqrtf(y);
+      q = (pn > 0.f && un > 0.f) ? tc * pn / un : 1.f;
+    }
+    if (threadIdx.x == 0) qs = q;
   }
+  __syncthreads();
+  const float q = qs;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
     const float p = a.p[t][i];
     float u = a.g[t][i] * gs;
@@ -219,10 +232,9 @@ extern "C" int ep_lars_step(int n, float* const* params, const float* const* gra
     if (numels[i] > mx) mx = numels[i];
   }
   cudaStream_t s = (cudaStream_t)stream;
-  EP_CUDA(cudaMemsetAsync(scratch, 0, 2 * n * sizeof(float), s));
   int bx = (int)((mx + 256 * 8 - 1) / (256 * 8));
   if (bx < 1) bx = 1;
-  if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+  if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;                  // 2 * n * bx <= EP_LARS_SCRATCH_FLOATS
   lars_norm_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch);
   EP_LAUNCH_CHECK();
   lars_update_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch);

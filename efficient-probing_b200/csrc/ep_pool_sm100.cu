@@ -428,6 +428,8 @@ __global__ void split_hilo_kernel(const float* __restrict__ src, float scale, in
 // one warp per (b, j/2) operand row pair of the logits: rowmax, rowsum = sum exp(S - rowmax), optional
 // attention map, and (blocks != nullptr) exp(S - rowmax) as bf16 hi/lo operand blocks for the pool-type
 // kernel -- tokens past N and row pairs past M are written as zeros, so the blocks need no memset.
+// kRegs > 0: the row (N <= 32 * kRegs) is held in registers -- one read, one exp per element.
+template <int kRegs>
 __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ S, int B, int M, int J, int N, int nkb,
                                                        float* __restrict__ rmax, float* __restrict__ rsum,
                                                        float* __restrict__ attn, uint8_t* __restrict__ blocks) {
@@ -436,8 +438,44 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
   if (r >= (long long)B * pairs) return;
   const int b = (int)(r / pairs), m = (int)(r % pairs);
   const int lane = threadIdx.x & 31;
-  float mx = 0.f, inv = 0.f;
   const float* row = S + ((size_t)b * M + min(m, M - 1)) * N;
+  const size_t blk_bytes = (size_t)J * 128;
+  if (kRegs > 0) {
+    float v[kRegs > 0 ? kRegs : 1];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) {
+      const int n = lane + 32 * k;
+      v[k] = (m < M && n < N) ? __ldg(row + n) : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) {
+      v[k] = (m < M && lane + 32 * k < N) ? __expf(v[k] - mx) : 0.f;
+      sum += v[k];
+    }
+    sum = warp_sum(sum);
+    if (m < M) {
+      if (lane == 0) { rmax[(size_t)b * M + m] = mx; rsum[(size_t)b * M + m] = sum; }
+      if (attn) {
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < kRegs; ++k)
+          if (lane + 32 * k < N) attn[((size_t)b * M + m) * N + lane + 32 * k] = v[k] * inv;
+      }
+    }
+    if (blocks) {
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k) {
+        const int n = lane + 32 * k;
+        if (n < nkb * kTokBlock) store_hilo(blocks + ((size_t)b * nkb + (n >> 6)) * blk_bytes, m, n & 63, v[k]);
+      }
+    }
+    return;
+  }
+  float mx = 0.f, inv = 0.f;
   if (m < M) {
     mx = -INFINITY;
     for (int n = lane; n < N; n += 32) mx = fmaxf(mx, row[n]);
@@ -453,7 +491,7 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
   if (blocks) {
     for (int n = lane; n < nkb * kTokBlock; n += 32) {
       const float e = (m < M && n < N) ? __expf(row[n] - mx) : 0.f;
-      store_hilo(blocks + ((size_t)b * nkb + (n >> 6)) * ((size_t)J * 128), m, n & 63, e);
+      store_hilo(blocks + ((size_t)b * nkb + (n >> 6)) * blk_bytes, m, n & 63, e);
     }
   }
 }
@@ -641,8 +679,14 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   if ((rc = launch_ks<0>(x, qhl, 0, B, N, D, M, pl, S, nullptr, nullptr, nullptr, nullptr, nullptr, 0, s))) return rc;
   tm.mark("ks<0> logits");
   const long long rows = (long long)B * (pl.J / 2);
-  rowstats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, B, M, pl.J, N, pl.nkb, rowmax, rowsum, attn,
-                                                            P ? blocks : nullptr);
+  {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    uint8_t* blk = P ? blocks : nullptr;
+    const int span = pl.nkb * kTokBlock;                       // tokens covered incl. the zero padding
+    if (span <= 32 * 10) rowstats_kernel<10><<<grid, 256, 0, s>>>(S, B, M, pl.J, N, pl.nkb, rowmax, rowsum, attn, blk);
+    else if (span <= 32 * 24) rowstats_kernel<24><<<grid, 256, 0, s>>>(S, B, M, pl.J, N, pl.nkb, rowmax, rowsum, attn, blk);
+    else rowstats_kernel<0><<<grid, 256, 0, s>>>(S, B, M, pl.J, N, pl.nkb, rowmax, rowsum, attn, blk);
+  }
   EP_LAUNCH_CHECK();
   tm.mark("rowstats");
   if (P == nullptr) return 0;

@@ -53,7 +53,7 @@ class LARS(torch.optim.Optimizer):
             key = (gi, dev)
             if key not in self._hyper:
                 self._hyper[key] = (torch.empty(_HYPER, dtype=torch.float32, device=dev),
-                                    torch.empty(16, dtype=torch.float32, device=dev))
+                                    torch.empty(8192, dtype=torch.float32, device=dev))
             hyper, scratch = self._hyper[key]
             hyper.copy_(torch.tensor([g["lr"], g["weight_decay"], g["momentum"], g["trust_coefficient"], 1.0],
                                      dtype=torch.float32), non_blocking=True)

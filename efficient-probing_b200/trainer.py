@@ -95,7 +95,7 @@ class EPHeadTrainer:
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
         self.hyper = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world], **f32)
         self.hyper_host = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world]).pin_memory()
-        self.lars_scratch = torch.empty(16, **f32)
+        self.lars_scratch = torch.empty(8192, **f32)       # EP_LARS_SCRATCH_FLOATS
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
         self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
@@ -283,27 +283,61 @@ class EPHeadTrainer:
         self._registered[(x.data_ptr(), targets.data_ptr())] = (x, targets)
 
     @torch.no_grad()
-    def train_step_host(self, x_host: torch.Tensor, targets_host: torch.Tensor, lr: Optional[float] = None) -> float:
+    def train_step_host(self, x_host: torch.Tensor, targets_host: torch.Tensor, lr: Optional[float] = None,
+                        next_x_host: Optional[torch.Tensor] = None,
+                        next_targets_host: Optional[torch.Tensor] = None) -> float:
         """End-to-end step from HOST buffers: pinned-memory H2D copy of tokens and labels, the step, and a
-        D2H read of the step's mean loss (the reference loop's samples.to(device) ... loss.item())."""
-        if not x_host.is_pinned():
+        D2H read of the step's mean loss (the reference loop's samples.to(device) ... loss.item()).
+
+        ``next_*``: the following step's host batch, if known -- its H2D copy is issued on a copy stream into
+        the other device slot right after this step is launched, so the 0.5 GB transfer of step i+1 overlaps
+        the kernels of step i (every batch still crosses PCIe exactly once, inside the caller's loop)."""
+        if self._hloss is None:
+            self._hloss = torch.empty(1, dtype=torch.float32).pin_memory()
+            self._h2d_stream = torch.cuda.Stream(device=self.dev)
+            self._slots = [(self.x, self.targets),
+                           (torch.empty_like(self.x), torch.empty_like(self.targets))]
+            for sx, st in self._slots:
+                self.register_batch(sx, st)
+            self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._prefetched = None           # (slot index, x_host data_ptr)
+            self._cur_slot = 0
+
+        def pin(xh, th):
+            if xh.is_pinned() and th.is_pinned():
+                return xh, th
             if self._hx is None:
                 self._hx = torch.empty(self.x.shape, dtype=self.x_dtype).pin_memory()
                 self._ht = torch.empty(self.B, dtype=torch.int64).pin_memory()
-            self._hx.copy_(x_host)
-            self._ht.copy_(targets_host)
-            x_host, targets_host = self._hx, self._ht
-        if self._hloss is None:
-            self._hloss = torch.empty(1, dtype=torch.float32).pin_memory()
+            self._hx.copy_(xh)
+            self._ht.copy_(th)
+            return self._hx, self._ht
+
+        cur = torch.cuda.current_stream(self.dev)
         if lr is not None:
             self.set_lr(lr)
-        self._cx, self._ct = self.x, self.targets
-        self.x.copy_(x_host, non_blocking=True)
-        self.targets.copy_(targets_host, non_blocking=True)
+        if self._prefetched is not None and self._prefetched[1] == x_host.data_ptr():
+            slot = self._prefetched[0]                       # already on its way: wait for the copy only
+            cur.wait_event(self._slot_ready[slot])
+        else:
+            slot = self._cur_slot
+            xh, th = pin(x_host, targets_host)
+            self._slots[slot][0].copy_(xh, non_blocking=True)
+            self._slots[slot][1].copy_(th, non_blocking=True)
+        self._prefetched = None
+        self._cx, self._ct = self._slots[slot]
         self._run()
         self.steps += 1
+        if next_x_host is not None and next_x_host.is_pinned() and next_targets_host.is_pinned():
+            other = slot ^ 1                                  # last read by step i-1, which has completed (sync below)
+            with torch.cuda.stream(self._h2d_stream):
+                self._slots[other][0].copy_(next_x_host, non_blocking=True)
+                self._slots[other][1].copy_(next_targets_host, non_blocking=True)
+                self._slot_ready[other].record(self._h2d_stream)
+            self._prefetched = (other, next_x_host.data_ptr())
+            self._cur_slot = other
         self._hloss.copy_(self.step_loss, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
+        cur.synchronize()
         return float(self._hloss[0])
 
     @torch.no_grad()

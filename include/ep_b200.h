@@ -140,8 +140,10 @@ int ep_ce_fwd_bwd(const float* logits, const long long* targets, int B, int K, f
  * of device pointers).  hyper is a DEVICE array {lr, weight_decay, momentum, trust_coefficient, grad_scale}
  * so a captured graph can be replayed with a new learning rate; grad_scale (1/world_size after a
  * sum all-reduce) multiplies every gradient first.  apply_trust_host[i] != 0 for tensors with
- * ndim > 1 (lars.py:21).  scratch: 2*n floats. */
+ * ndim > 1 (lars.py:21).  scratch: EP_LARS_SCRATCH_FLOATS floats (per-CTA partial norms, summed in a fixed
+ * order: the update is bit-reproducible run to run). */
 #define EP_LARS_MAX_TENSORS 8
+#define EP_LARS_SCRATCH_FLOATS 8192
 int ep_lars_step(int n, float* const* params_host, const float* const* grads_host, float* const* mus_host,
                  const long long* numels_host, const int* apply_trust_host, const float* hyper,
                  float* scratch, void* stream);

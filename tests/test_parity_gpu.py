@@ -196,3 +196,29 @@ def test_errors_are_loud():
     with pytest.raises(NotImplementedError):
         out.sum().backward()
     assert E._lib.load().ep_device_check() == 0
+
+
+def test_host_buffer_step_matches_device_step():
+    """train_step_host (pinned host buffers, prefetch of the next batch) == train_step on resident tensors."""
+    B, N, D, M, K = 16, 65, 128, 8, 24
+    xs = [O.synthetic_tokens(B, N, D, seed=40 + i) for i in range(3)]
+    ys = [O.synthetic_labels(B, K, seed=50 + i) for i in range(3)]
+    torch.manual_seed(0)
+    h1 = E.make_ep_head(D, M, K).to(DEV)
+    torch.manual_seed(0)
+    h2 = E.make_ep_head(D, M, K).to(DEV)
+    t1 = E.EPHeadTrainer(h1, B, N, lr=0.5, use_graph=True)
+    t2 = E.EPHeadTrainer(h2, B, N, lr=0.5, use_graph=True)
+    hx = [x.pin_memory() for x in xs]
+    hy = [y.pin_memory() for y in ys]
+    for i in range(3):
+        t1.train_step(xs[i].to(DEV), ys[i].to(DEV))
+        l1 = float(t1.step_loss)
+        nxt = (i + 1) % 3
+        l2 = t2.train_step_host(hx[i], hy[i], next_x_host=hx[nxt], next_targets_host=hy[nxt])
+        assert abs(l1 - l2) <= 1e-6 * abs(l1), (i, l1, l2)
+    l3 = t2.train_step_host(xs[0], ys[0])                 # pageable host tensors are staged through pinned memory
+    t1.train_step(xs[0].to(DEV), ys[0].to(DEV))
+    assert abs(float(t1.step_loss) - l3) <= 1e-6 * abs(l3)
+    for p1, p2 in zip(h1.parameters(), h2.parameters()):
+        assert torch.equal(p1, p2)
