@@ -333,11 +333,12 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   int rc;
   StageTimer tm(s);
   LinWs lw;
-  const bool tc = use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw);
+  const bool aligned = use_tc() && F % 4 == 0 && K % 4 == 0;
+  const bool tc = aligned && lin_ws(workspace, workspace_bytes, B, F, K, &lw);   // dy needs the operand copies
   (void)0;
   if (dW) {
     if (!y) return EP_ERR_NULL;
-    if (tc) {                      // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: batch-major operands, "TN" kernel
+    if (aligned) {                 // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: batch-major operands, "TN" kernel
       if ((rc = launch_gemm_tn(dlogits, y, dW, K, F, B, 1, K, F, F, 0, 0, 0, s))) return rc;
       tm.mark("lin dW tn-gemm");
     } else {

@@ -99,6 +99,7 @@ class EPHeadTrainer:
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
         self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
+        self.side_stream = torch.cuda.Stream(device=dev)
         self._cx, self._ct = self.x, self.targets           # the batch the next launch sequence reads
         self._registered = {}                               # (x ptr, targets ptr) -> (x, targets) kept alive
         self.graphs = {}                                    # (x ptr, targets ptr) -> captured step
@@ -135,15 +136,24 @@ class EPHeadTrainer:
         _lib.check(lib.ep_ce_fwd_bwd(self.logits.data_ptr(), self._ct.data_ptr(), B, K, 1.0 / B, 1.0 / B,
                                      self.step_loss.data_ptr(), self.dlogits.data_ptr(), self.correct.data_ptr(), s),
                    "ep_ce_fwd_bwd")
+        # classifier gradients: dW/db need only (dlogits, y) and nothing downstream needs them before the
+        # exchange, so they run on a side stream (a parallel branch of the captured graph) next to the dy chain
+        cur = torch.cuda.current_stream(self.dev)
+        self.side_stream.wait_stream(cur)
+        with torch.cuda.stream(self.side_stream):
+            _lib.check(lib.ep_linear_bwd(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
+                                         self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), None,
+                                         None, 0, _lib.stream_ptr(self.dev)), "ep_linear_bwd (dW, db)")
         _lib.check(lib.ep_linear_bwd(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
-                                     self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), self.dy.data_ptr(),
-                                     self.lin_ws.data_ptr(), self.lin_ws.numel(), s), "ep_linear_bwd")
+                                     None, None, self.dy.data_ptr(),
+                                     self.lin_ws.data_ptr(), self.lin_ws.numel(), s), "ep_linear_bwd (dy)")
         _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
                                  self.dout.data_ptr(), s), "ep_bn_bwd")
         d_vb = self.g["v_b"].data_ptr() if pool.v.bias is not None else None
         _lib.check(lib.ep_bwd_proj(self.dout.data_ptr(), self.P.data_ptr(), pool.v.weight.data_ptr(), _lib.x_dtype_code(self._cx),
                                    B, N, D, M, self.d_out, self.g["v_w"].data_ptr(), d_vb, self.ws.data_ptr(), self.ws.numel(), s),
                    "ep_bwd_proj")
+        cur.wait_stream(self.side_stream)
 
     def _part2(self):
         """token-streaming half of the backward pass: d cls_token"""
