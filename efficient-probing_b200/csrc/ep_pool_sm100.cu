@@ -39,7 +39,7 @@ constexpr int kBrickBytes = 2 * kTokBlock * 128;   // [64 tokens x 128 d] = two 
 constexpr int kSmemBudget = 220 * 1024;
 
 struct KSParams {
-  int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols, nkb, ndelta, x_keep;
+  int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols, nkb, ndelta;
   float* out;            // mode 0: logits (B, M, N)
   uint8_t* blocks;       // mode 1: dS as operand blocks [B][nkb][J rows x 64 tokens] bf16 hi/lo, swizzled
   const float* S;        // mode 1: saved logits
@@ -123,16 +123,9 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), w_bytes + (uint32_t)gt * kXChunkBytes);
           tma_load_3d(dst, &tm_w, full_bar(s), c * kChunkD, 0, p.w_batched ? b : 0);
-          for (int t = 0; t < gt; ++t) {
-            // the tail of the batch is left in L2 for the pool-type kernel that follows (it walks the
-            // samples in reverse); everything earlier is streamed evict-first
-            if (p.x_keep && item >= nitems - p.x_keep)
-              tma_load_3d(dst + w_bytes + (uint32_t)t * kXChunkBytes, &tm_x, full_bar(s), c * kChunkD,
-                          (t0 + t) * kTileRows, b);
-            else
-              tma_load_3d_hint(dst + w_bytes + (uint32_t)t * kXChunkBytes, &tm_x, full_bar(s), c * kChunkD,
-                               (t0 + t) * kTileRows, b, pol_x);
-          }
+          for (int t = 0; t < gt; ++t)
+            tma_load_3d_hint(dst + w_bytes + (uint32_t)t * kXChunkBytes, &tm_x, full_bar(s), c * kChunkD,
+                             (t0 + t) * kTileRows, b, pol_x);
           if (++s == p.nstages) { s = 0; ph ^= 1u; }
         }
       }
@@ -287,8 +280,7 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
       const uint64_t pol_x = policy_evict_first();
       int s = 0, ws = 0;
       uint32_t ph = 0, wph = 0;
-      for (int br = blockIdx.x; br < p.B; br += gridDim.x) {
-        const int b = p.B - 1 - br;                           // reverse order: newest tokens first (still in L2)
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(wempty(ws), wph ^ 1u);                    // operand block of this token block
           mbar_arrive_expect_tx(wfull(ws), wt_bytes);
@@ -381,11 +373,11 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
     };
     if (kMode == 0) {
       int it = 0;
-      for (int br = blockIdx.x; br < p.B; br += gridDim.x, ++it) {
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
         const int buf = it % p.nbuf;
         mbar_wait(afull(buf), ((uint32_t)(it / p.nbuf)) & 1u);
         tc_fence_after();
-        drain(buf, p.B - 1 - br);
+        drain(buf, b);
         tc_fence_before();
         mbar_arrive(aempty(buf));
       }
@@ -613,10 +605,6 @@ int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, 
   p.nchunks = D / kChunkD; p.nstages = pl.ks_stages; p.w_batched = w_batched; p.nbuf = pl.ks_nbuf;
   p.bufcols = pl.G * pl.J; p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
   p.nkb = pl.nkb; p.ndelta = ndelta;
-  {  // items (sample x tile group) at the end of the batch whose tokens (~96 MB) stay in L2
-    const size_t item_bytes = (size_t)pl.G * kTileRows * D * 2;
-    p.x_keep = (g_debug & 512) ? 0 : (int)std::min<size_t>((size_t)B * pl.ngroups, ((size_t)96 << 20) / item_bytes);
-  }
   p.out = out; p.blocks = blocks; p.S = S; p.rmax = rmax; p.rsum = rsum; p.delta = delta;
   if ((rc = set_dyn_smem(ks_kernel<kMode>, pl.ks_smem))) return rc;
   const int grid = std::min(B * pl.ngroups, kNumSMs);
