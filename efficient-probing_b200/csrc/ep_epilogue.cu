@@ -186,9 +186,97 @@ __global__ void __launch_bounds__(256) lars_update_kernel(LarsArgs a, const floa
   }
 }
 
+// ---------------- AdamW / SGD (main_linprobe.py:403-408: {"lars": LARS, "adamw": AdamW}, else SGD) ----------------
+struct OptArgs {
+  float* p[EP_LARS_MAX_TENSORS];
+  const float* g[EP_LARS_MAX_TENSORS];
+  float* s1[EP_LARS_MAX_TENSORS];     // AdamW: exp_avg; SGD: momentum_buffer
+  float* s2[EP_LARS_MAX_TENSORS];     // AdamW: exp_avg_sq
+  long long n[EP_LARS_MAX_TENSORS];
+};
+
+// torch.optim.AdamW (decoupled weight decay).  hyper = {lr, beta1, beta2, eps, weight_decay, grad_scale,
+// bias_correction1 = 1 - beta1^t, bias_correction2 = 1 - beta2^t}
+__global__ void __launch_bounds__(256) adamw_kernel(OptArgs a, const float* __restrict__ hyper) {
+  const int t = blockIdx.y;
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
+  const float step_size = lr / hyper[6], inv_bc2_sqrt = rsqrtf(hyper[7]);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
+    const float g = a.g[t][i] * gs;
+    float p = a.p[t][i] * (1.f - lr * wd);
+    const float m = b1 * a.s1[t][i] + (1.f - b1) * g;
+    const float v = b2 * a.s2[t][i] + (1.f - b2) * g * g;
+    a.s1[t][i] = m;
+    a.s2[t][i] = v;
+    p -= step_size * m / (sqrtf(v) * inv_bc2_sqrt + eps);
+    a.p[t][i] = p;
+  }
+}
+
+// torch.optim.SGD (dampening 0, no nesterov).  hyper = {lr, weight_decay, momentum, grad_scale, first_step}
+__global__ void __launch_bounds__(256) sgd_kernel(OptArgs a, const float* __restrict__ hyper) {
+  const int t = blockIdx.y;
+  const float lr = hyper[0], wd = hyper[1], mom = hyper[2], gs = hyper[3];
+  const bool first = hyper[4] != 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
+    const float p = a.p[t][i];
+    float d = fmaf(wd, p, a.g[t][i] * gs);
+    if (mom != 0.f && a.s1[t]) {
+      d = first ? d : fmaf(mom, a.s1[t][i], d);
+      a.s1[t][i] = d;
+    }
+    a.p[t][i] = fmaf(-lr, d, p);
+  }
+}
+
 }  // namespace ep
 
 using namespace ep;
+
+namespace {
+int fill_opt_args(OptArgs* a, int n, float* const* params, const float* const* grads, float* const* s1, float* const* s2,
+                  const long long* numels, bool need_s1, bool need_s2, long long* mx) {
+  if (n <= 0 || n > EP_LARS_MAX_TENSORS) return EP_ERR_SHAPE;
+  if (!params || !grads || !numels || (need_s1 && !s1) || (need_s2 && !s2)) return EP_ERR_NULL;
+  *mx = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!params[i] || !grads[i] || (need_s1 && !s1[i]) || (need_s2 && !s2[i])) return EP_ERR_NULL;
+    a->p[i] = params[i]; a->g[i] = grads[i]; a->s1[i] = s1 ? s1[i] : nullptr; a->s2[i] = s2 ? s2[i] : nullptr;
+    a->n[i] = numels[i];
+    if (numels[i] > *mx) *mx = numels[i];
+  }
+  return 0;
+}
+int opt_grid(long long mx) {
+  int bx = (int)((mx + 256 * 8 - 1) / (256 * 8));
+  return bx < 1 ? 1 : (bx > 2 * kNumSMs ? 2 * kNumSMs : bx);
+}
+}  // namespace
+
+extern "C" int ep_adamw_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const long long* numels, const float* hyper, void* stream) {
+  OptArgs a;
+  long long mx;
+  if (!hyper) return EP_ERR_NULL;
+  int rc = fill_opt_args(&a, n, params, grads, exp_avg, exp_avg_sq, numels, true, true, &mx);
+  if (rc) return rc;
+  adamw_kernel<<<dim3(opt_grid(mx), n), 256, 0, (cudaStream_t)stream>>>(a, hyper);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ep_sgd_step(int n, float* const* params, const float* const* grads, float* const* momentum_buf,
+                           const long long* numels, const float* hyper, void* stream) {
+  OptArgs a;
+  long long mx;
+  if (!hyper) return EP_ERR_NULL;
+  int rc = fill_opt_args(&a, n, params, grads, momentum_buf, nullptr, numels, false, false, &mx);
+  if (rc) return rc;
+  sgd_kernel<<<dim3(opt_grid(mx), n), 256, 0, (cudaStream_t)stream>>>(a, hyper);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
 
 extern "C" int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum, int training, float* running_mean,
                          float* running_var, long long* nbt, float* y, float* save_mean, float* save_invstd,

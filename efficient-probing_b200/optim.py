@@ -25,6 +25,35 @@ def lars_launch(params, grads, mus, trust_flags, hyper_dev, scratch):
     _lib.check(rc, "ep_lars_step")
 
 
+def _ptr_table(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def adamw_launch(params, grads, exp_avg, exp_avg_sq, hyper_dev):
+    """One fused torch.optim.AdamW update for up to 8 fp32 CUDA tensors (hyper: see ep_adamw_step)."""
+    lib = _lib.load()
+    n = len(params)
+    Nn = (ctypes.c_longlong * n)(*[p.numel() for p in params])
+    dev = params[0].device
+    with torch.cuda.device(dev):
+        rc = lib.ep_adamw_step(n, _ptr_table(params), _ptr_table(grads), _ptr_table(exp_avg), _ptr_table(exp_avg_sq), Nn,
+                               hyper_dev.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(rc, "ep_adamw_step")
+
+
+def sgd_launch(params, grads, momentum_bufs, hyper_dev):
+    """One fused torch.optim.SGD update (dampening 0, no nesterov); momentum_bufs may be None."""
+    lib = _lib.load()
+    n = len(params)
+    Nn = (ctypes.c_longlong * n)(*[p.numel() for p in params])
+    dev = params[0].device
+    with torch.cuda.device(dev):
+        rc = lib.ep_sgd_step(n, _ptr_table(params), _ptr_table(grads),
+                             _ptr_table(momentum_bufs) if momentum_bufs is not None else None, Nn,
+                             hyper_dev.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(rc, "ep_sgd_step")
+
+
 class LARS(torch.optim.Optimizer):
     """LARS optimizer, no rate scaling or weight decay for parameters <= 1D (util/lars.py:4-37).
 

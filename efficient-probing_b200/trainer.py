@@ -25,7 +25,7 @@ from torch import nn
 from . import _lib
 from .ep import EfficientProbing
 from .flatgrad import FlatGradLayout, allreduce_sum_
-from .optim import lars_launch
+from .optim import lars_launch, adamw_launch, sgd_launch
 
 BN_EPS_DEFAULT = 1e-6
 
@@ -34,7 +34,16 @@ class EPHeadTrainer:
     def __init__(self, head: nn.Sequential, batch_size: int, num_tokens: int, *, lr: float = 0.1,
                  weight_decay: float = 0.0, momentum: float = 0.9, trust_coefficient: float = 0.001,
                  x_dtype: torch.dtype = torch.bfloat16, process_group=None, use_graph: bool = True,
-                 overlap_comm: bool = True):
+                 overlap_comm: bool = True, optimizer: str = "lars", betas=(0.9, 0.999), eps: float = 1e-8,
+                 accum_iter: int = 1):
+        """optimizer: "lars" (util/lars.py, the published protocol), "adamw" (torch.optim.AdamW defaults) or "sgd"
+        (torch.optim.SGD, momentum as given) -- the three main_linprobe.py:403-408 can build.
+        accum_iter: gradient accumulation as engine_finetune.py:72-77 (loss / accum_iter, optimizer every k-th call)."""
+        if optimizer not in ("lars", "adamw", "sgd"):
+            raise ValueError("optimizer must be 'lars', 'adamw' or 'sgd'")
+        if optimizer == "sgd" and momentum == 0.9 and False:
+            pass
+        self.optimizer, self.betas, self.eps_opt, self.accum_iter = optimizer, betas, eps, max(1, int(accum_iter))
         pool, bn, fc = head[0], head[1], head[2]
         if not isinstance(pool, EfficientProbing) or not isinstance(bn, nn.BatchNorm1d) or not isinstance(fc, nn.Linear):
             raise TypeError("head must be Sequential(EfficientProbing, BatchNorm1d, Linear) (probe_heads.py:106)")
@@ -74,7 +83,15 @@ class EPHeadTrainer:
         self.n_early = self.layout.early
         self.grads = [self.g["cls"], self.g["v_w"]] + ([self.g["v_b"]] if pool.v.bias is not None else []) + \
                      [self.g["fc_w"], self.g["fc_b"]]
-        self.mus = [torch.zeros_like(p) for p in self.params]
+        self.mus = [torch.zeros_like(p) for p in self.params]           # LARS mu / SGD momentum_buffer / AdamW exp_avg
+        self.sq = [torch.zeros_like(p) for p in self.params] if optimizer == "adamw" else None   # AdamW exp_avg_sq
+        self.opt_steps = 0
+        self.accum = torch.zeros_like(self.flat_grad) if self.accum_iter > 1 else None
+        if self.accum is not None:
+            av = self.layout.views(self.accum)
+            self._accum_grads = [av["cls"], av["v_w"]] + ([av["v_b"]] if pool.v.bias is not None else []) + \
+                                [av["fc_w"], av["fc_b"]]
+        self.micro = 0
         # activations
         self.x = torch.empty(B, N, D, dtype=x_dtype, device=dev)
         self.targets = torch.empty(B, dtype=torch.int64, device=dev)
@@ -93,8 +110,10 @@ class EPHeadTrainer:
         self.loss_sum = torch.zeros(1, **f32)            # running sum of per-step mean losses
         self.step_loss = torch.zeros(1, **f32)           # mean loss of the last step
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.hyper = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world], **f32)
-        self.hyper_host = torch.tensor([lr, weight_decay, momentum, trust_coefficient, 1.0 / self.world]).pin_memory()
+        self._lr, self._wd, self._mom, self._trust = float(lr), float(weight_decay), float(momentum), float(trust_coefficient)
+        self.hyper_host = torch.zeros(8)                   # pageable on purpose: the H2D copy stages it at call time,
+        self.hyper = torch.zeros(8, **f32)                 # so rewriting it for the next step cannot race the GPU
+        self._write_hyper()
         self.lars_scratch = torch.empty(8192, **f32)       # EP_LARS_SCRATCH_FLOATS
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
         self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
@@ -165,8 +184,49 @@ class EPHeadTrainer:
                                    self.ws.data_ptr(), self.ws.numel(), s), "ep_bwd_pool")
 
     def _part3(self):
-        lars_launch(self.params, self.grads, self.mus, self.trust, self.hyper, self.lars_scratch)
+        if self.accum is not None:                         # engine_finetune.py:72-77
+            self.accum.add_(self.flat_grad)
+            self.loss_sum.add_(self.step_loss)
+            return
+        self._apply_optimizer(self.grads)
         self.loss_sum.add_(self.step_loss)
+
+    def _apply_optimizer(self, grads):
+        if self.optimizer == "lars":
+            lars_launch(self.params, grads, self.mus, self.trust, self.hyper, self.lars_scratch)
+        elif self.optimizer == "adamw":
+            adamw_launch(self.params, grads, self.mus, self.sq, self.hyper)
+        else:
+            sgd_launch(self.params, grads, self.mus if self._mom != 0.0 else None, self.hyper)
+
+    def _write_hyper(self):
+        """Host scalars of the next optimizer step -> pinned -> device (stream-ordered, no sync)."""
+        gs = 1.0 / (self.world * self.accum_iter)
+        h = self.hyper_host
+        if self.optimizer == "lars":
+            h[:5] = torch.tensor([self._lr, self._wd, self._mom, self._trust, gs])
+        elif self.optimizer == "adamw":
+            t = self.opt_steps + 1
+            h[:8] = torch.tensor([self._lr, self.betas[0], self.betas[1], self.eps_opt, self._wd, gs,
+                                  1.0 - self.betas[0] ** t, 1.0 - self.betas[1] ** t], dtype=torch.float64).float()
+        else:
+            h[:5] = torch.tensor([self._lr, self._wd, self._mom, gs, 1.0 if self.opt_steps == 0 else 0.0])
+        self.hyper.copy_(h)
+
+    def _after_run(self):
+        """Host-side bookkeeping after one (micro-)step has been enqueued."""
+        self.micro += 1
+        if self.accum is not None:
+            if self.micro % self.accum_iter == 0:          # engine_finetune.py:73-77: step + zero_grad every k-th call
+                self._apply_optimizer(self._accum_grads)
+                self.accum.zero_()
+                self.opt_steps += 1
+                if self.optimizer != "lars":
+                    self._write_hyper()
+        else:
+            self.opt_steps += 1
+            if self.optimizer != "lars":                   # bias corrections / first-step flag change every step
+                self._write_hyper()
 
     def _exchange_early(self):
         """[fc, v] gradients are final after part 1: reduce them underneath part 2 on the comm stream"""
@@ -239,16 +299,23 @@ class EPHeadTrainer:
 
     def _snapshot(self):
         bn = self.bn
-        return ([p.detach().clone() for p in self.params], [m.clone() for m in self.mus], bn.running_mean.clone(),
+        return ([p.detach().clone() for p in self.params], [m.clone() for m in self.mus],
+                [q.clone() for q in self.sq] if self.sq is not None else None,
+                self.accum.clone() if self.accum is not None else None, bn.running_mean.clone(),
                 bn.running_var.clone(), bn.num_batches_tracked.clone(), self.loss_sum.clone(), self.correct.clone())
 
     def _restore(self, snap):
-        ps, ms, rm, rv, nbt, ls, cr = snap
+        ps, ms, sq, acc, rm, rv, nbt, ls, cr = snap
         with torch.no_grad():
             for p, q in zip(self.params, ps):
                 p.copy_(q)
             for m, q in zip(self.mus, ms):
                 m.copy_(q)
+            if sq is not None:
+                for m, q in zip(self.sq, sq):
+                    m.copy_(q)
+            if acc is not None:
+                self.accum.copy_(acc)
             self.bn.running_mean.copy_(rm)
             self.bn.running_var.copy_(rv)
             self.bn.num_batches_tracked.copy_(nbt)
@@ -258,10 +325,10 @@ class EPHeadTrainer:
     # ------------------------------------------------------------------ public API
     def set_lr(self, lr: float, weight_decay: Optional[float] = None):
         """Host scalar from the schedule (util/lr_sched.py) -> device, without a sync."""
-        self.hyper_host[0] = lr
+        self._lr = float(lr)
         if weight_decay is not None:
-            self.hyper_host[1] = weight_decay
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+            self._wd = float(weight_decay)
+        self._write_hyper()
 
     @torch.no_grad()
     def train_step(self, x: torch.Tensor, targets: torch.Tensor, lr: Optional[float] = None):
@@ -281,6 +348,7 @@ class EPHeadTrainer:
             if targets.data_ptr() != self.targets.data_ptr():
                 self.targets.copy_(targets, non_blocking=True)
         self._run()
+        self._after_run()
         self.steps += 1
 
     def register_batch(self, x: torch.Tensor, targets: torch.Tensor):
@@ -337,6 +405,7 @@ class EPHeadTrainer:
         self._prefetched = None
         self._cx, self._ct = self._slots[slot]
         self._run()
+        self._after_run()
         self.steps += 1
         if next_x_host is not None and next_x_host.is_pinned() and next_targets_host.is_pinned():
             other = slot ^ 1                                  # last read by step i-1, which has completed (sync below)
@@ -376,18 +445,44 @@ class EPHeadTrainer:
         self.steps = 0
 
     def optimizer_state_dict(self):
-        """torch.optim-style state for util/misc.py:322 checkpoints: state[i]['mu'] in parameters() order."""
-        return {"state": {i: {"mu": m.clone()} for i, m in enumerate(self.mus)},
-                "param_groups": [{"lr": float(self.hyper_host[0]), "weight_decay": float(self.hyper_host[1]),
-                                  "momentum": float(self.hyper_host[2]), "trust_coefficient": float(self.hyper_host[3]),
-                                  "params": list(range(len(self.params)))}]}
+        """torch.optim-style state for util/misc.py:322 checkpoints, indexed in parameters() order:
+        LARS {'mu'}, SGD {'momentum_buffer'}, AdamW {'step', 'exp_avg', 'exp_avg_sq'}."""
+        state = {}
+        for i, m in enumerate(self.mus):
+            if self.optimizer == "lars":
+                state[i] = {"mu": m.clone()}
+            elif self.optimizer == "sgd":
+                state[i] = {"momentum_buffer": m.clone()} if self._mom != 0.0 else {}
+            else:
+                state[i] = {"step": torch.tensor(float(self.opt_steps)), "exp_avg": m.clone(), "exp_avg_sq": self.sq[i].clone()}
+        group = {"lr": self._lr, "weight_decay": self._wd, "params": list(range(len(self.params)))}
+        if self.optimizer == "lars":
+            group.update(momentum=self._mom, trust_coefficient=self._trust)
+        elif self.optimizer == "sgd":
+            group.update(momentum=self._mom, dampening=0, nesterov=False)
+        else:
+            group.update(betas=tuple(self.betas), eps=self.eps_opt)
+        return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):
+        key = {"lars": "mu", "sgd": "momentum_buffer", "adamw": "exp_avg"}[self.optimizer]
         for i, m in enumerate(self.mus):
             st = sd["state"].get(i, sd["state"].get(str(i)))
-            if st is not None and "mu" in st:
-                m.copy_(st["mu"].to(m.device))
+            if st is None:
+                continue
+            if key in st:
+                m.copy_(st[key].to(m.device))
+            if self.optimizer == "adamw":
+                if "exp_avg_sq" in st:
+                    self.sq[i].copy_(st["exp_avg_sq"].to(m.device))
+                if "step" in st:
+                    self.opt_steps = int(float(st["step"]))
+            elif key in st:
+                self.opt_steps = max(self.opt_steps, 1)
         g = sd["param_groups"][0]
-        self.hyper_host[0], self.hyper_host[1] = g["lr"], g["weight_decay"]
-        self.hyper_host[2], self.hyper_host[3] = g.get("momentum", 0.9), g.get("trust_coefficient", 0.001)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._lr, self._wd = float(g["lr"]), float(g["weight_decay"])
+        if self.optimizer != "adamw":
+            self._mom = float(g.get("momentum", self._mom))
+        if self.optimizer == "lars":
+            self._trust = float(g.get("trust_coefficient", self._trust))
+        self._write_hyper()

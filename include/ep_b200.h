@@ -148,6 +148,17 @@ int ep_lars_step(int n, float* const* params_host, const float* const* grads_hos
                  const long long* numels_host, const int* apply_trust_host, const float* hyper,
                  float* scratch, void* stream);
 
+/* The other two optimizers main_linprobe.py:403-408 can build ({"lars": LARS, "adamw": AdamW}, else SGD), one
+ * launch for all tensors; pointer tables are HOST arrays of device pointers, hyper is a DEVICE array.
+ * ep_adamw_step -- torch.optim.AdamW: hyper = {lr, beta1, beta2, eps, weight_decay, grad_scale,
+ *                  1 - beta1^t, 1 - beta2^t} (the two bias corrections of step t, computed by the host).
+ * ep_sgd_step   -- torch.optim.SGD (dampening 0, no nesterov): hyper = {lr, weight_decay, momentum, grad_scale,
+ *                  first_step != 0}; momentum_buf_host may be NULL when momentum == 0. */
+int ep_adamw_step(int n, float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                  float* const* exp_avg_sq_host, const long long* numels_host, const float* hyper, void* stream);
+int ep_sgd_step(int n, float* const* params_host, const float* const* grads_host, float* const* momentum_buf_host,
+                const long long* numels_host, const float* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

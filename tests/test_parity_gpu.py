@@ -222,3 +222,53 @@ def test_host_buffer_step_matches_device_step():
     assert abs(float(t1.step_loss) - l3) <= 1e-6 * abs(l3)
     for p1, p2 in zip(h1.parameters(), h2.parameters()):
         assert torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("opt", ["adamw", "sgd", "sgd_nomom"])
+def test_other_optimizers_match_torch(opt):
+    """main_linprobe.py:403-408 builds AdamW or SGD besides LARS: the fused kernels follow torch.optim."""
+    B, N, D, M, K = 16, 33, 128, 8, 10
+    p = O.build_head(D, M, K, seed=0)
+    p.cls_token = p.cls_token * 10.0
+    head = head_from_params(p, K)
+    ref_head = head_from_params(p, K)
+    mom = 0.0 if opt == "sgd_nomom" else 0.9
+    kw = dict(lr=0.05, weight_decay=0.01, use_graph=True)
+    tr = E.EPHeadTrainer(head, B, N, optimizer="adamw" if opt == "adamw" else "sgd", momentum=mom, **kw)
+    ropt = (torch.optim.AdamW(ref_head.parameters(), lr=0.05, weight_decay=0.01) if opt == "adamw" else
+            torch.optim.SGD(ref_head.parameters(), lr=0.05, weight_decay=0.01, momentum=mom))
+    ref_head.train()
+    for it in range(4):
+        x = O.synthetic_tokens(B, N, D, seed=70 + it).to(DEV)
+        y = O.synthetic_labels(B, K, seed=80 + it).to(DEV)
+        tr.train_step(x, y)
+        ropt.zero_grad()
+        nn.CrossEntropyLoss()(ref_head(x), y).backward()      # the drop-in module + torch BN/Linear/CE/optimizer
+        ropt.step()
+    for (k, a), (_, b) in zip(head.named_parameters(), ref_head.named_parameters()):
+        close(a.detach(), b.detach(), 2e-3, f"{opt} {k}")
+    sd = tr.optimizer_state_dict()
+    assert set(sd["state"][0]) == ({"step", "exp_avg", "exp_avg_sq"} if opt == "adamw" else
+                                   ({"momentum_buffer"} if mom else set()))
+
+
+def test_accum_iter_matches_large_batch_gradient():
+    """engine_finetune.py:72-77: k micro-steps with loss / k, then one optimizer step."""
+    B, N, D, M, K = 8, 20, 128, 8, 10
+    p = O.build_head(D, M, K, seed=0)
+    xs = [O.synthetic_tokens(B, N, D, seed=90 + i).to(DEV) for i in range(2)]
+    ys = [O.synthetic_labels(B, K, seed=95 + i).to(DEV) for i in range(2)]
+    h_acc, h_ref = head_from_params(p, K), head_from_params(p, K)
+    tr = E.EPHeadTrainer(h_acc, B, N, lr=0.1, accum_iter=2, use_graph=True)
+    before = [q.detach().clone() for q in h_acc.parameters()]
+    tr.train_step(xs[0], ys[0])
+    for q, b in zip(h_acc.parameters(), before):
+        assert torch.equal(q, b)                               # no update after the first micro-step
+    tr.train_step(xs[1], ys[1])
+    opt = E.LARS(h_ref.parameters(), lr=0.1)
+    h_ref.train()
+    for x, y in zip(xs, ys):
+        (nn.CrossEntropyLoss()(h_ref(x), y) / 2).backward()
+    opt.step()
+    for (k, a), (_, b) in zip(h_acc.named_parameters(), h_ref.named_parameters()):
+        close(a.detach(), b.detach(), 1e-3, "accum " + k)
