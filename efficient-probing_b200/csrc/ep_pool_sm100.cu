@@ -40,6 +40,7 @@ constexpr int kSmemBudget = 220 * 1024;
 
 struct KSParams {
   int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols, nkb, ndelta;
+  int tail_rows;         // > 0: the last token tile of a sample is loaded as this many rows only (single tile group)
   float* out;            // mode 0: logits (B, M, N)
   uint8_t* blocks;       // mode 1: dS as operand blocks [B][nkb][J rows x 64 tokens] bf16 hi/lo, swizzled
   const float* S;        // mode 1: saved logits
@@ -81,13 +82,19 @@ __device__ __forceinline__ void store_hilo(uint8_t* blk, int m, int t, float e) 
 // ------------------------------------------------------------------------------------------------
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
-ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const KSParams p) {
+ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xt,
+          const __grid_constant__ CUtensorMap tm_w, const KSParams p) {
+  // smem: [barriers, 1 KB][stage 0][stage 1]...[16 KB slack].  A stage = operand chunk + the x chunks of the
+  // sample's token tiles; with tail_rows the last tile holds only its valid rows (rounded to 8): the MMA still
+  // reads 128 rows there -- the rows past the tail come from whatever follows in shared memory (next stage or
+  // the slack) and only reach accumulator rows n >= N, which the epilogue never uses.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = bar_base + 1024u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_bytes = (uint32_t)p.J * 128u;
-  const uint32_t stage_bytes = w_bytes + (uint32_t)p.G * kXChunkBytes;
-  const uint32_t bar_base = smem_base + (uint32_t)p.nstages * stage_bytes;
+  const uint32_t tail_bytes = p.tail_rows ? (uint32_t)p.tail_rows * 128u : (uint32_t)kXChunkBytes;
+  const uint32_t stage_bytes = w_bytes + (uint32_t)(p.G - 1) * kXChunkBytes + tail_bytes;
   // barriers: full[nstages], empty[nstages], tmem_full[2], tmem_empty[2], then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.nstages + s); };
@@ -102,7 +109,7 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_xt); prefetch_tmap(&tm_w); }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -121,11 +128,13 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
-          mbar_arrive_expect_tx(full_bar(s), w_bytes + (uint32_t)gt * kXChunkBytes);
+          const bool tail = p.tail_rows != 0;                 // (single group: the last tile of the item is the tail)
+          mbar_arrive_expect_tx(full_bar(s), w_bytes + (uint32_t)(gt - 1) * kXChunkBytes +
+                                                 (tail ? tail_bytes : (uint32_t)kXChunkBytes));
           tma_load_3d(dst, &tm_w, full_bar(s), c * kChunkD, 0, p.w_batched ? b : 0);
           for (int t = 0; t < gt; ++t)
-            tma_load_3d_hint(dst + w_bytes + (uint32_t)t * kXChunkBytes, &tm_x, full_bar(s), c * kChunkD,
-                             (t0 + t) * kTileRows, b, pol_x);
+            tma_load_3d_hint(dst + w_bytes + (uint32_t)t * kXChunkBytes, (tail && t == gt - 1) ? &tm_xt : &tm_x,
+                             full_bar(s), c * kChunkD, (t0 + t) * kTileRows, b, pol_x);
           if (++s == p.nstages) { s = 0; ph ^= 1u; }
         }
       }
@@ -537,7 +546,7 @@ int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 
 struct Plan {
   bool ok = false;
-  int J, ntiles, G, ngroups, ks_stages, ks_nbuf, nkb, nsl_fwd, nsl_bwd, ysplit_fwd, ysplit_bwd, xslots, wslots;
+  int J, ntiles, G, ngroups, ks_stages, ks_nbuf, nkb, nsl_fwd, nsl_bwd, ysplit_fwd, ysplit_bwd, xslots, wslots, tail_rows;
   size_t ks_smem, kp_smem;
 };
 
@@ -553,10 +562,14 @@ Plan make_plan(int N, int D, int M) {
   pl.ngroups = (pl.ntiles + G - 1) / G;
   G = (pl.ntiles + pl.ngroups - 1) / pl.ngroups;            // balance the groups
   pl.G = G;
-  const size_t stage = (size_t)pl.J * 128 + (size_t)G * kXChunkBytes;
-  pl.ks_stages = (int)std::min<size_t>(6, kSmemBudget / stage);
+  // ragged last tile: load only its valid rows (multiple of 8 = one swizzle atom) when one group covers the sample
+  const int rem = N - (pl.ntiles - 1) * kTileRows;
+  pl.tail_rows = (pl.ngroups == 1 && rem < kTileRows) ? (rem + 7) / 8 * 8 : 0;
+  const size_t stage = (size_t)pl.J * 128 + (size_t)(G - 1) * kXChunkBytes +
+                       (pl.tail_rows ? (size_t)pl.tail_rows * 128 : (size_t)kXChunkBytes);
+  pl.ks_stages = (int)std::min<size_t>(8, (kSmemBudget - kXChunkBytes) / stage);
   pl.ks_nbuf = (2 * G * pl.J <= 512) ? 2 : 1;
-  pl.ks_smem = pl.ks_stages * stage + 1024 + 256;
+  pl.ks_smem = 1024 /*alignment*/ + 1024 /*barriers*/ + pl.ks_stages * stage + kXChunkBytes /*slack*/;
   pl.nkb = (N + kTokBlock - 1) / kTokBlock;
   const int slices = D / 128;
   const int max_sl_fwd = std::max(1, 256 / pl.J), max_sl_bwd = std::max(1, 512 / pl.J);   // fwd double-buffers TMEM
@@ -596,19 +609,20 @@ template <int kMode>
 int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, int M, const Plan& pl, float* out,
               uint8_t* blocks, const float* S, const float* rmax, const float* rsum, const float* delta, int ndelta,
               cudaStream_t s) {
-  CUtensorMap tm_x, tm_w;
+  CUtensorMap tm_x, tm_xt, tm_w;
   int rc;
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTileRows))) return rc;
+  if ((rc = make_tmap(&tm_xt, x, D, N, B, pl.tail_rows ? pl.tail_rows : kTileRows))) return rc;
   if ((rc = make_tmap(&tm_w, w, D, pl.J, w_batched ? B : 1, pl.J))) return rc;
   KSParams p{};
   p.B = B; p.N = N; p.D = D; p.M = M; p.J = pl.J; p.ntiles = pl.ntiles; p.G = pl.G; p.ngroups = pl.ngroups;
   p.nchunks = D / kChunkD; p.nstages = pl.ks_stages; p.w_batched = w_batched; p.nbuf = pl.ks_nbuf;
   p.bufcols = pl.G * pl.J; p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
-  p.nkb = pl.nkb; p.ndelta = ndelta;
+  p.nkb = pl.nkb; p.ndelta = ndelta; p.tail_rows = pl.tail_rows;
   p.out = out; p.blocks = blocks; p.S = S; p.rmax = rmax; p.rsum = rsum; p.delta = delta;
   if ((rc = set_dyn_smem(ks_kernel<kMode>, pl.ks_smem))) return rc;
   const int grid = std::min(B * pl.ngroups, kNumSMs);
-  ks_kernel<kMode><<<grid, kThreads, pl.ks_smem, s>>>(tm_x, tm_w, p);
+  ks_kernel<kMode><<<grid, kThreads, pl.ks_smem, s>>>(tm_x, tm_xt, tm_w, p);
   EP_LAUNCH_CHECK();
   return 0;
 }
