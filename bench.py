@@ -282,7 +282,7 @@ def main():
                                 float(pool_mod.scale), B, N, D, M, 1, tr.out.data_ptr(), tr.S.data_ptr(),
                                 tr.rowmax.data_ptr(), tr.rowsum.data_ptr(), tr.P.data_ptr(), None, tr.ws.data_ptr(),
                                 tr.ws.numel(), s), "ep_fwd")
-        E._lib.check(lib.ep_bwd_proj(tr.dout.data_ptr(), tr.P.data_ptr(), pool_mod.v.weight.data_ptr(), xt, B, N, D, M, 1,
+        E._lib.check(lib.ep_bwd_proj(tr.dout.data_ptr(), tr.P.data_ptr(), tr.out.data_ptr(), pool_mod.v.weight.data_ptr(), None, xt, B, N, D, M, 1,
                                      tr.g["v_w"].data_ptr(), None, tr.ws.data_ptr(), tr.ws.numel(), s), "ep_bwd_proj")
         E._lib.check(lib.ep_bwd_pool(x.data_ptr(), xt, pool_mod.cls_token.data_ptr(), float(pool_mod.scale), B, N, D, M,
                                      1, tr.S.data_ptr(), tr.rowmax.data_ptr(), tr.rowsum.data_ptr(),

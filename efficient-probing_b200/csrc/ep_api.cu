@@ -83,7 +83,6 @@ int lin_nt(int rows, int cols) {
   return 64;
 }
 int dp_nt(int D) { return std::min(128, (D + 31) / 32 * 32); }     // column tile of the fused dP GEMM
-int col_tiles(int D) { return 2 * ((D + dp_nt(D) - 1) / dp_nt(D)); }   // delta partials: two per column tile
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
@@ -91,7 +90,7 @@ Ws carve(int B, int N, int D, int M) {
   w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
   w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
-  w.delta = off; off += align_up((size_t)64 * B * M * sizeof(float), 256);   // up to 64 delta partials
+  w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
   w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
   w.sm100 = off; off += align_up(sm100_workspace_bytes(B, N, D, M), 256);
   w.total = off;
@@ -156,10 +155,10 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   return launch_gemm_v0(g, s);
 }
 
-extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int x_dtype, int B, int N, int D,
-                           int M, int d_out, float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes,
-                           void* stream) {
-  if (!g_out || !P || !v_w || !d_v_w) return EP_ERR_NULL;
+extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out, const float* v_w, const float* v_b,
+                           int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (!g_out || !P || !out || !v_w || !d_v_w) return EP_ERR_NULL;
   if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
   const Ws w = carve(B, N, D, M);
   if (!workspace || workspace_bytes < w.total) return EP_ERR_WORKSPACE;
@@ -169,6 +168,8 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
   const int Dp = D / d_out, c = Dp / M;
   int rc;
   StageTimer tm(s);
+  // delta[b, m] = sum_n A dA = dP[b, m] . P[b, m] = g[b, m, :] . (out[b, m, :] - bias[m, :])
+  if ((rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
   if (use_tc() && c % 4 == 0) {
     // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch, both operands
     // batch-major -> TF32 mma.sync "TN" kernel reading them as they lie
@@ -186,14 +187,14 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
       TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1, bf};
       TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1, bf};
       int fam_rc = 0;
-      if (use_sm100(x_dtype, B, N, D, M, &fam_rc) && col_tiles(D) <= 64) {
+      if (use_sm100(x_dtype, B, N, D, M, &fam_rc)) {
         // tcgen05 pooling kernels follow: the GEMM epilogue emits what they consume -- dP as bf16 hi/lo operand
-        // rows and delta = dP . P as per-column-tile partials -- and fp32 dP is never written
+        // rows -- and fp32 dP is never written
         void* sm = (char*)workspace + w.sm100;
         const int J = sm100_J(N, D, M);
         void* hl = sm100_dphl_ptr(sm, B, N, D, M);
         if (J != 2 * M) EP_CUDA(cudaMemsetAsync(hl, 0, (size_t)B * J * D * 2, s));
-        if ((rc = tc_gemm_dp(A, Bm, B, D, 3 * c, M, dp_nt(D), P, hl, delta, J, s))) return rc;
+        if ((rc = tc_gemm_dp(A, Bm, B, D, 3 * c, M, dp_nt(D), hl, J, s))) return rc;
         tm.mark("dP tc-gemm+hl");
         return 0;
       }
@@ -201,9 +202,7 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
       if ((rc = tc_gemm(A, Bm, B, D, 3 * c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
       tm.mark("dP tc-gemm");
     }
-    rc = launch_rowdot(dP, P, (long long)B * M, D, delta, s);
-    tm.mark("rowdot");
-    return rc;
+    return 0;
   }
   {  // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]
     GemmDesc g{};
@@ -224,7 +223,7 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* v_w,
     g.c_i = (long long)M * D; g.c_j = 1; g.c_z = D;
     if ((rc = launch_gemm_v0(g, s))) return rc;
   }
-  return launch_rowdot(dP, P, (long long)B * M, D, delta, s);   // delta = sum_n A dA = dP . P
+  return 0;
 }
 
 extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M,
@@ -242,9 +241,9 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
     const int c = D / d_out / M;
-    const bool fused = use_tc() && c % 4 == 0 && col_tiles(D) <= 64;      // what ep_bwd_proj did (same predicate)
-    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, fused ? nullptr : dP, delta,
-                          fused ? col_tiles(D) : 1, d_cls_token, (char*)workspace + w.sm100, s);
+    const bool fused = use_tc() && c % 4 == 0;                            // what ep_bwd_proj did (same predicate)
+    return sm100_pool_bwd(x, S, scale, B, N, D, M, rowmax, rowsum, fused ? nullptr : dP, delta, 1, d_cls_token,
+                          (char*)workspace + w.sm100, s);
   }
   if (rc) return rc;
   t_last_family = 1;
@@ -254,12 +253,13 @@ extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, f
 
 extern "C" int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale, int B, int N,
                       int D, int M, int d_out, const float* S, const float* rowmax, const float* rowsum,
-                      const float* P, const float* g_out, float* d_cls_token, float* d_v_w, float* d_v_b,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* P, const float* out, const float* v_b, const float* g_out, float* d_cls_token,
+                      float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
-  if (!v_w || !S || !rowmax || !rowsum || !P || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
-  if ((rc = ep_bwd_proj(g_out, P, v_w, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace, workspace_bytes, stream)))
+  if (!v_w || !S || !rowmax || !rowsum || !P || !out || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
+  if ((rc = ep_bwd_proj(g_out, P, out, v_w, v_b, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace, workspace_bytes,
+                        stream)))
     return rc;
   return ep_bwd_pool(x, x_dtype, cls_token, scale, B, N, D, M, d_out, S, rowmax, rowsum, d_cls_token, workspace,
                      workspace_bytes, stream);

@@ -102,6 +102,8 @@ struct GemmDesc {      // C[z][i][j] = sum_k A[z][i][k] * B[z][k][j] (+ bias[z][
 };
 int launch_gemm_v0(const GemmDesc& g, cudaStream_t s);
 int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s);            // out[j] = sum_i a[i][j]
+int launch_delta_from_out(const float* g, const float* out, const float* bias, long long rows, int M, int c,
+                          float* delta, cudaStream_t s);
 int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s);  // out[i] = a[i].b[i]
 
 // TF32 tensor-core GEMM (ep_gemm_sm100.cu)
@@ -132,9 +134,8 @@ int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias,
                     long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z,
                     long long bias_z, cudaStream_t s);
 
-// projection backward with the fused epilogue: dP as bf16 hi/lo rows (B, Jrows, D) + ceil(J/NT) partial deltas
-int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, const float* P, void* hl,
-               float* delta_part, int Jrows, cudaStream_t s);
+// projection backward with the fused epilogue: dP written as bf16 hi/lo operand rows (B, Jrows, D)
+int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, void* hl, int Jrows, cudaStream_t s);
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s);

@@ -33,13 +33,10 @@ struct GemmTC {
   int stages;                                 // smem ring depth
   int bf16;                                   // operands are bf16 (kind::f16, 64 elements per stage) instead of fp32/tf32
   // epilogue mode 1 (projection backward, C = dP[b, z=m, d]): instead of storing fp32 dP, write it as the
-  // bf16 hi/lo operand rows (B, Jrows, D) the dA kernel consumes and the partial delta = sum_d dP * P of this
-  // column tile -- dP never touches memory in fp32
+  // bf16 hi/lo operand rows (B, Jrows, D) the dA kernel consumes -- dP never touches memory in fp32
   int epi_mode;
-  const float* P;                             // (B, Mq, D)
   __nv_bfloat16* hl;                          // (B, Jrows, D)
-  float* delta_part;                          // (gridDim.x, B * Mq)
-  int Mq, Jrows;
+  int Jrows;
 };
 
 __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
@@ -184,31 +181,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int row = i0 + wq * 32 + lane;
       const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * g.NT);
       if (g.epi_mode == 1) {
-        // row = sample b, z = query m, columns = d (J == D)
-        const float* prow = g.P + ((size_t)row * g.Mq + z) * g.J;
+        // row = sample b, z = query m, columns = d (J == D): dP leaves TMEM as bf16 hi/lo operand rows
         __nv_bfloat16* hrow = g.hl + ((size_t)row * g.Jrows + 2 * z) * g.J;
-        float dsum = 0.f;
-        const bool rok = row < g.I;
-        float4 pv[2][4];
-        auto load_p = [&](int c0, float4 (&dst)[4]) {
-          const int col = j0 + c0;
-          if (rok && c0 < g.NT && col + 16 <= g.J) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(prow + col) + q);
-          }
-        };
-        auto emit = [&](int c0, const float4 (&src)[4]) {
+        for (int c0 = 16 * eh; c0 < g.NT; c0 += 32) {
           uint32_t r[16];
           tmem_ld16(acc + (uint32_t)c0, r);
           tmem_ld_wait();
           const int col = j0 + c0;
-          if (rok && col + 16 <= g.J) {
-            const float* pf = reinterpret_cast<const float*>(src);
+          if (row < g.I && col + 16 <= g.J) {
             __align__(16) __nv_bfloat16 hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float v = __uint_as_float(r[i]);
-              dsum = fmaf(v, pf[i], dsum);
               hi[i] = __float2bfloat16_rn(v);
               lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
             }
@@ -217,17 +201,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             reinterpret_cast<uint4*>(hrow + g.J + col)[0] = reinterpret_cast<const uint4*>(lo)[0];
             reinterpret_cast<uint4*>(hrow + g.J + col)[1] = reinterpret_cast<const uint4*>(lo)[1];
           }
-        };
-        // the P loads of the next 16 columns are in flight while the current ones are converted
-        load_p(16 * eh, pv[0]);
-        for (int c0 = 16 * eh; c0 < g.NT; c0 += 64) {
-          load_p(c0 + 32, pv[1]);
-          emit(c0, pv[0]);
-          load_p(c0 + 64, pv[0]);
-          if (c0 + 32 < g.NT) emit(c0 + 32, pv[1]);
         }
-        // two partials per column tile (one per epilogue warp group)
-        if (rok) g.delta_part[((size_t)(j0 / g.NT) * 2 + eh) * g.I * g.Mq + (size_t)row * g.Mq + z] = dsum;
       } else {
         float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
         const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
@@ -335,8 +309,8 @@ static int side_tmap(CUtensorMap* m, const TcSide& sd, int tile_rows) {
   return make_tmap_f32(m, sd.base, sd.d0, sd.d1, sd.d2, sd.s1, sd.s2, sd.swap ? 1u : r, sd.swap ? r : 1u, sd.bf16);
 }
 
-int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, const float* P, void* hl,
-               float* delta_part, int Jrows, cudaStream_t s) {
+int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, void* hl, int Jrows,
+               cudaStream_t s) {
   CUtensorMap ta, tb;
   int rc;
   if ((rc = side_tmap(&ta, A, 128))) return rc;
@@ -345,7 +319,7 @@ int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int
   g.I = I; g.J = J; g.K = K; g.NT = NT;
   g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
-  g.epi_mode = 1; g.P = P; g.hl = (__nv_bfloat16*)hl; g.delta_part = delta_part; g.Mq = Z; g.Jrows = Jrows;
+  g.epi_mode = 1; g.hl = (__nv_bfloat16*)hl; g.Jrows = Jrows;
   g.bf16 = A.bf16;
   return launch_gemm_tc(ta, tb, g, Z, s);
 }

@@ -109,6 +109,29 @@ __global__ void rowdot_kernel(const float* __restrict__ a, const float* __restri
   s = warp_sum(s);
   if (lane == 0) out[r] = s;
 }
+// delta[b, m] = sum_j g[b, m*c + j] * (out[b, m*c + j] - bias[m*c + j]).  Since out - bias = W_m . P[b, m], this
+// equals dP[b, m] . P[b, m] = sum_n A dA (the softmax-backward row term) without touching the (B, M, D) tensors.
+__global__ void delta_from_out_kernel(const float* __restrict__ g, const float* __restrict__ out,
+                                      const float* __restrict__ bias, long long rows, int M, int c,
+                                      float* __restrict__ delta) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // r = b * M + m
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int m = (int)(r % M);
+  const float* gp = g + r * c;            // (B, M*c) row-major: element (b, m*c + j) sits at (b*M + m)*c + j
+  const float* op = out + r * c;
+  float s = 0.f;
+  for (int j = lane; j < c; j += 32) s = fmaf(__ldg(gp + j), __ldg(op + j) - (bias ? __ldg(bias + m * c + j) : 0.f), s);
+  s = warp_sum(s);
+  if (lane == 0) delta[r] = s;
+}
+int launch_delta_from_out(const float* g, const float* out, const float* bias, long long rows, int M, int c,
+                          float* delta, cudaStream_t s) {
+  delta_from_out_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(g, out, bias, rows, M, c, delta);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s) {
   rowdot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a, b, rows, cols, out);
   EP_LAUNCH_CHECK();

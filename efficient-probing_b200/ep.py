@@ -51,7 +51,7 @@ class EPPoolFunction(torch.autograd.Function):
                             rowsum.data_ptr(), P.data_ptr(), _lib.ptr(attn), ws.data_ptr(), ws.numel(),
                             _lib.stream_ptr(dev))
         _lib.check(rc, "ep_fwd")
-        ctx.save_for_backward(x, cls32, w32, S, rowmax, rowsum, P)
+        ctx.save_for_backward(x, cls32, w32, S, rowmax, rowsum, P, out, b32)
         ctx.meta = (float(scale), M, int(d_out), v_bias is not None, cls_token.dtype, v_weight.dtype)
         ctx.x_needs_grad = x.requires_grad
         if return_attn:
@@ -65,7 +65,7 @@ class EPPoolFunction(torch.autograd.Function):
             raise NotImplementedError("dL/dx is not produced: the EP probe trains on a frozen backbone "
                                       "(main_linprobe.py:393-400); --finetuning is out of scope")
         lib = _lib.load()
-        x, cls32, w32, S, rowmax, rowsum, P = ctx.saved_tensors
+        x, cls32, w32, S, rowmax, rowsum, P, out, b32 = ctx.saved_tensors
         scale, M, d_out, has_bias, cls_dtype, w_dtype = ctx.meta
         B, N, D = x.shape
         dev = x.device
@@ -77,7 +77,7 @@ class EPPoolFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             rc = lib.ep_bwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), scale,
                             B, N, D, M, d_out, S.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(),
-                            g.data_ptr(),
+                            out.data_ptr(), _lib.ptr(b32), g.data_ptr(),
                             d_cls.data_ptr(), d_w.data_ptr(), _lib.ptr(d_b), ws.data_ptr(), ws.numel(),
                             _lib.stream_ptr(dev))
         _lib.check(rc, "ep_bwd")

@@ -169,7 +169,8 @@ class EPHeadTrainer:
         _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
                                  self.dout.data_ptr(), s), "ep_bn_bwd")
         d_vb = self.g["v_b"].data_ptr() if pool.v.bias is not None else None
-        _lib.check(lib.ep_bwd_proj(self.dout.data_ptr(), self.P.data_ptr(), pool.v.weight.data_ptr(), _lib.x_dtype_code(self._cx),
+        _lib.check(lib.ep_bwd_proj(self.dout.data_ptr(), self.P.data_ptr(), self.out.data_ptr(), pool.v.weight.data_ptr(),
+                                   _lib.ptr(pool.v.bias), _lib.x_dtype_code(self._cx),
                                    B, N, D, M, self.d_out, self.g["v_w"].data_ptr(), d_vb, self.ws.data_ptr(), self.ws.numel(), s),
                    "ep_bwd_proj")
         cur.wait_stream(self.side_stream)

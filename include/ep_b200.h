@@ -84,22 +84,26 @@ int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w,
            void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of ep_fwd (replaces autograd through ep.py:35-45; engine_finetune.py:73 -> misc.py:267).
- * g_out = dL/d out (B, D/d_out).  Writes d_cls_token (M, D), d_v_w (D/d_out, D), d_v_b (D/d_out,
- * nullable).  The frozen-backbone path needs no dL/dx (main_linprobe.py:393-400). */
+ * g_out = dL/d out (B, D/d_out); out = what ep_fwd returned and v_b the bias it used (nullable) -- the
+ * softmax-backward row term sum_n A dA equals g . (out - v_b) per query, so no pass over P is needed for it.
+ * Writes d_cls_token (M, D), d_v_w (D/d_out, D), d_v_b (D/d_out, nullable).  The frozen-backbone path needs
+ * no dL/dx (main_linprobe.py:393-400). */
 int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale,
            int B, int N, int D, int M, int d_out,
-           const float* S, const float* rowmax, const float* rowsum, const float* P, const float* g_out,
+           const float* S, const float* rowmax, const float* rowsum, const float* P, const float* out,
+           const float* v_b, const float* g_out,
            float* d_cls_token, float* d_v_w, float* d_v_b,
            void* workspace, size_t workspace_bytes, void* stream);
 
 /* The two halves of ep_bwd, for callers that overlap the gradient all-reduce with the token-streaming
  * half (the DDP bucket overlap of main_linprobe.py:581-583, done explicitly):
- *   ep_bwd_proj : needs only g_out and the saved P -- writes d_v_w, d_v_b (99% of the EP gradient bytes)
- *                 and leaves dP = g_out . v_w and delta = dP . P in the workspace;
+ *   ep_bwd_proj : needs only g_out, out and the saved P -- writes d_v_w, d_v_b (99% of the EP gradient bytes)
+ *                 and leaves dP = g_out . v_w and delta = g_out . (out - v_b) in the workspace;
  *   ep_bwd_pool : streams x once, recomputes A, writes d_cls_token.  Must follow ep_bwd_proj on the
  *                 same stream with the same workspace. */
-int ep_bwd_proj(const float* g_out, const float* P, const float* v_w, int x_dtype, int B, int N, int D, int M,
-                int d_out, float* d_v_w, float* d_v_b, void* workspace, size_t workspace_bytes, void* stream);
+int ep_bwd_proj(const float* g_out, const float* P, const float* out, const float* v_w, const float* v_b, int x_dtype,
+                int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
+                void* workspace, size_t workspace_bytes, void* stream);
 int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M, int d_out,
                 const float* S, const float* rowmax, const float* rowsum, float* d_cls_token,
                 void* workspace, size_t workspace_bytes, void* stream);

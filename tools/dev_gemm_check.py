@@ -27,7 +27,7 @@ for (B, N, D, M, d_out) in [(256, 5, 256, 8, 1), (130, 3, 128, 32, 1), (64, 4, 2
     ws = torch.empty(lib.ep_workspace_bytes(B, N, D, M, d_out), dtype=torch.uint8, device=dev)
     _lib.check(lib.ep_fwd(x.data_ptr(), 0, cls.data_ptr(), W.data_ptr(), None, D ** -0.5, B, N, D, M, d_out, out.data_ptr(), S.data_ptr(), rm.data_ptr(), rs.data_ptr(), P.data_ptr(), None, ws.data_ptr(), ws.numel(), s()), "ep_fwd")
     g = torch.randn(B, Dp, device=dev); dvw = torch.empty(Dp, D, device=dev)
-    _lib.check(lib.ep_bwd_proj(g.data_ptr(), P.data_ptr(), W.data_ptr(), 1, B, N, D, M, d_out, dvw.data_ptr(), None, ws.data_ptr(), ws.numel(), s()), "bwd_proj")
+    _lib.check(lib.ep_bwd_proj(g.data_ptr(), P.data_ptr(), out.data_ptr(), W.data_ptr(), None, 1, B, N, D, M, d_out, dvw.data_ptr(), None, ws.data_ptr(), ws.numel(), s()), "bwd_proj")
     torch.cuda.synchronize()
     Wm = W.double().reshape(M, c, D)
     ref_out = torch.einsum("mjc,bmc->bmj", Wm, P.double()).reshape(B, Dp)

@@ -32,7 +32,7 @@ stages = {
  "ce": lambda x: lib.ep_ce_fwd_bwd(tr.logits.data_ptr(), tr.targets.data_ptr(), B, K, 1.0 / B, 1.0 / B, tr.step_loss.data_ptr(), tr.dlogits.data_ptr(), tr.correct.data_ptr(), s()),
  "linear_bwd": lambda x: lib.ep_linear_bwd(tr.dlogits.data_ptr(), tr.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K, tr.g["fc_w"].data_ptr(), tr.g["fc_b"].data_ptr(), tr.dy.data_ptr(), tr.lin_ws.data_ptr(), tr.lin_ws.numel(), s()),
  "bn_bwd": lambda x: lib.ep_bn_bwd(tr.dy.data_ptr(), tr.y.data_ptr(), tr.save_invstd.data_ptr(), B, Dp, tr.dout.data_ptr(), s()),
- "bwd_proj": lambda x: lib.ep_bwd_proj(tr.dout.data_ptr(), tr.P.data_ptr(), pl.v.weight.data_ptr(), xt, B, N, D, M, 1, tr.g["v_w"].data_ptr(), None, tr.ws.data_ptr(), tr.ws.numel(), s()),
+ "bwd_proj": lambda x: lib.ep_bwd_proj(tr.dout.data_ptr(), tr.P.data_ptr(), tr.out.data_ptr(), pl.v.weight.data_ptr(), None, xt, B, N, D, M, 1, tr.g["v_w"].data_ptr(), None, tr.ws.data_ptr(), tr.ws.numel(), s()),
  "bwd_pool": lambda x: lib.ep_bwd_pool(x.data_ptr(), xt, pl.cls_token.data_ptr(), float(pl.scale), B, N, D, M, 1, tr.S.data_ptr(), tr.rowmax.data_ptr(), tr.rowsum.data_ptr(), tr.g["cls"].data_ptr(), tr.ws.data_ptr(), tr.ws.numel(), s()),
  "lars": lambda x: (lars_launch(tr.params, tr.grads, tr.mus, tr.trust, tr.hyper, tr.lars_scratch), 0)[1],
 }
