@@ -82,7 +82,7 @@ int lin_nt(int rows, int cols) {
     if (rt * ((cols + nt - 1) / nt) >= kNumSMs / 2 || nt == 64) return nt;
   return 64;
 }
-int dp_nt(int D) { return std::min(128, (D + 31) / 32 * 32); }     // column tile of the fused dP GEMM
+int dp_nt(int D) { return std::min(256, (D + 31) / 32 * 32); }     // column tile of the fused dP GEMM
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;

@@ -37,6 +37,7 @@ struct GemmTC {
   int epi_mode;
   __nv_bfloat16* hl;                          // (B, Jrows, D)
   int Jrows;
+  int debug;
 };
 
 __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
@@ -60,6 +61,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// 256-bit global store (sm_100: STG.E.256): 32-byte aligned address
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ float to_tf32(float v) {
   uint32_t r;
@@ -189,39 +196,36 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tmem_ld_wait();
           const int col = j0 + c0;
           if (row < g.I && col + 16 <= g.J) {
-            __align__(16) __nv_bfloat16 hi[16], lo[16];
+            __align__(32) __nv_bfloat16 hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float v = __uint_as_float(r[i]);
               hi[i] = __float2bfloat16_rn(v);
               lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
             }
-            reinterpret_cast<uint4*>(hrow + col)[0] = reinterpret_cast<const uint4*>(hi)[0];
-            reinterpret_cast<uint4*>(hrow + col)[1] = reinterpret_cast<const uint4*>(hi)[1];
-            reinterpret_cast<uint4*>(hrow + g.J + col)[0] = reinterpret_cast<const uint4*>(lo)[0];
-            reinterpret_cast<uint4*>(hrow + g.J + col)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            st_global_256(hrow + col, reinterpret_cast<const uint32_t*>(hi));          // one full 32-byte sector
+            st_global_256(hrow + g.J + col, reinterpret_cast<const uint32_t*>(lo));    // per lane and store
           }
         }
       } else {
         float* crow = g.C + (long long)z * g.c_z + (long long)row * g.c_row;
         const float* bias = g.bias ? g.bias + (long long)z * g.bias_z : nullptr;
-        const bool vec = g.c_col == 1 && (g.c_row % 4) == 0 && (g.c_z % 4) == 0 && (j0 % 4) == 0 &&
-                         ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+        const bool vec = g.c_col == 1 && (g.c_row % 8) == 0 && (g.c_z % 8) == 0 && (j0 % 8) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(g.C) & 31) == 0);
         for (int c0 = 16 * eh; c0 < g.NT; c0 += 32) {
           uint32_t r[16];
           tmem_ld16(acc + (uint32_t)c0, r);
           tmem_ld_wait();
           if (row < g.I) {
             if (vec && j0 + c0 + 16 <= g.J) {                  // 64 contiguous bytes per lane
-              float v[16];
+              __align__(32) float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + j0 + c0 + i) : 0.f);
                 if (g.round_tf32) v[i] = to_tf32(v[i]);
               }
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(crow + j0 + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              st_global_256(crow + j0 + c0, reinterpret_cast<const uint32_t*>(v));         // full 32-byte sectors
+              st_global_256(crow + j0 + c0 + 8, reinterpret_cast<const uint32_t*>(v) + 8);
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -319,7 +323,7 @@ int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int
   g.I = I; g.J = J; g.K = K; g.NT = NT;
   g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
-  g.epi_mode = 1; g.hl = (__nv_bfloat16*)hl; g.Jrows = Jrows;
+  g.epi_mode = 1; g.hl = (__nv_bfloat16*)hl; g.Jrows = Jrows; g.debug = g_debug;
   g.bf16 = A.bf16;
   return launch_gemm_tc(ta, tb, g, Z, s);
 }
