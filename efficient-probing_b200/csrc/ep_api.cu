@@ -66,7 +66,7 @@ extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count;
 
 namespace {
 struct Ws {                      // workspace layout
-  size_t dP, delta, slots, sm100, w_r, w_t, g_r, total;
+  size_t dP, delta, slots, sm100, w_r, w_t, g_r, g_t, total;
 };
 // The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
@@ -89,6 +89,7 @@ Ws carve(int B, int N, int D, int M) {
   w.w_r = off;   off += 0;                                                   // (unused)
   w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
   w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
+  w.g_t = off;   off += align_up((size_t)3 * B * D * 2, 256);               // bf16 [hi|hi|lo] copy of g_out^T
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
   w.delta = off; off += align_up((size_t)B * M * sizeof(float), 256);
   w.slots = off; off += align_up((size_t)kDqSlots * M * D * sizeof(float), 256);
@@ -105,6 +106,15 @@ int check_common(const void* x, int x_dtype, const float* cls, int B, int N, int
   if (((uintptr_t)x & 15) || ((uintptr_t)cls & 15)) return EP_ERR_ALIGN;
   return 0;
 }
+bool use_sm100(int x_dtype, int B, int N, int D, int M, int* rc);
+// P (the saved pooled tokens) is kept as bf16 hi/lo rows (b, m, {hi, lo}, d) -- byte-for-byte the size of the fp32
+// tensor -- when the tcgen05 kernels produce and consume it: the projection and its weight gradient then read
+// it in place as the 3-term bf16 operand ([hi|lo|hi] along the contraction) of tcgen05 GEMMs.
+bool p_hilo(int x_dtype, int B, int N, int D, int M, int d_out) {
+  int rc = 0;
+  const int c = D / d_out / M;
+  return use_tc() && kSplitBf16 && c % 8 == 0 && D % 64 == 0 && B % 64 == 0 && use_sm100(x_dtype, B, N, D, M, &rc);
+}
 bool use_sm100(int x_dtype, int B, int N, int D, int M, int* rc) {
   *rc = 0;
   if (g_kernel_mode == 1) return false;
@@ -120,6 +130,11 @@ extern "C" size_t ep_workspace_bytes(int B, int N, int D, int M, int d_out) {
   return carve(B, N, D, M).total;
 }
 
+extern "C" int ep_pooled_layout(int x_dtype, int B, int N, int D, int M, int d_out) {
+  if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % d_out || (D / d_out) % M) return EP_ERR_SHAPE;
+  return p_hilo(x_dtype, B, N, D, M, d_out) ? 1 : 0;
+}
+
 extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
                       float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
                       float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
@@ -129,9 +144,7 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   const Ws w = carve(B, N, D, M);
   if (w.total > 0 && (!workspace || workspace_bytes < w.total)) return EP_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  // P stays exact fp32: it is also the saved tensor behind delta = dP . P in the backward pass, and the TF32
-  // GEMM that consumes it tolerates the hardware's truncation of this one operand (the weight side is rounded)
-  const int round_p = 0;
+  const int round_p = p_hilo(x_dtype, B, N, D, M, d_out) ? 1 : 0;   // P as bf16 hi/lo rows (see p_hilo)
   if (use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
     rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p,
@@ -144,7 +157,22 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   if (rc) return rc;
   // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
   const int Dp = D / d_out, c = Dp / M;
-  if (use_tc() && D % 4 == 0)       // P is too large to copy: 3xTF32 in registers (mma.sync), P read once
+  if (round_p) {
+    // tcgen05 3-term bf16 GEMM: A = P's hi/lo rows read in place, B = [W_hi | W_hi | W_lo] (a 6*D'*D-byte copy
+    // whose first and last thirds are the hi/lo pair)
+    void* w3f = (char*)workspace + w.w_t;
+    StageTimer tm(s);
+    if ((rc = launch_split3(v_w, w3f, Dp, D, D, 1, 1, s))) return rc;
+    tm.mark("proj split3 W");
+    const unsigned long long D3 = 3ull * D;
+    TcSide A{P, (unsigned long long)D, 2ull * M, (unsigned long long)B, (unsigned long long)D, 2ull * M * D, TC_KMAJOR, 1, 1,
+             1, 2, 1, 0};
+    TcSide Bm{w3f, D3, (unsigned long long)c, (unsigned long long)M, D3, D3 * c, TC_KMAJOR, 0, 1, 1, 0, 0, 2 * D};
+    rc = tc_gemm(A, Bm, B, c, D, M, round_nt(c), out, Dp, 1, c, v_b, c, 0, s);
+    tm.mark("proj tc-gemm");
+    return rc;
+  }
+  if (use_tc() && D % 4 == 0)       // fp32 P: 3xTF32 in registers (mma.sync), P read once
     return launch_gemm_nt3(P, v_w, out, v_b, B, c, D, M, (long long)M * D, D, Dp, D, (long long)c * D, c, c, s);
   GemmDesc g{};
   g.A = P; g.B = v_w; g.C = out; g.bias = v_b;
@@ -171,10 +199,24 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
   // delta[b, m] = sum_n A dA = dP[b, m] . P[b, m] = g[b, m, :] . (out[b, m, :] - bias[m, :])
   if ((rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
   if (use_tc() && c % 4 == 0) {
-    // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch, both operands
-    // batch-major -> TF32 mma.sync "TN" kernel reading them as they lie
-    if ((rc = launch_gemm_tn(g_out, P, d_v_w, c, D, B, M, Dp, (long long)M * D, D, c, D, (long long)c * D, s))) return rc;
-    tm.mark("dW tn-gemm");
+    // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch
+    if (p_hilo(x_dtype, B, N, D, M, d_out)) {
+      // tcgen05 3-term bf16 GEMM: rows d, cols j, contraction over b.  A = P's hi/lo rows in place, MN-major
+      // (channels contiguous); B = g^T as [g_hi | g_hi | g_lo] (K-major copy, 6*B*D' bytes)
+      void* g3t = (char*)workspace + w.g_t;
+      if ((rc = launch_split3_transpose(g_out, g3t, B, Dp, 1, 0, 0, 1, 1, s))) return rc;     // [Dp][3B]
+      tm.mark("dW split3t g");
+      const unsigned long long B3 = 3ull * B;
+      TcSide A{P, (unsigned long long)D, 2ull * M, (unsigned long long)B, (unsigned long long)D, 2ull * M * D, TC_MNMAJOR, 1,
+               1, 1, 2, 1, 0};
+      TcSide Bm{g3t, B3, (unsigned long long)c, (unsigned long long)M, B3, B3 * c, TC_KMAJOR, 0, 1, 1, 0, 0, 2 * B};
+      if ((rc = tc_gemm(A, Bm, D, c, B, M, round_nt(c), d_v_w, 1, D, (long long)c * D, nullptr, 0, 0, s))) return rc;
+      tm.mark("dW tc-gemm");
+    } else {
+      // fp32 P, both operands batch-major -> TF32 mma.sync "TN" kernel reading them as they lie
+      if ((rc = launch_gemm_tn(g_out, P, d_v_w, c, D, B, M, Dp, (long long)M * D, D, c, D, (long long)c * D, s))) return rc;
+      tm.mark("dW tn-gemm");
+    }
     if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
     {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05, 3xTF32 (dP drives the query gradient)
       float* g3 = (float*)((char*)workspace + w.g_r);              // [(b, m)][3c]  = [big | small | big]

@@ -119,6 +119,9 @@ struct TcSide {            // one operand as a 3-D fp32 tensor (d0 contiguous) a
   int swap;                // 0: dim1 = rows-or-k, dim2 = batch; 1: dim1 = batch, dim2 = rows-or-k
   int zdiv;                // batch coordinate = z / zdiv
   int bf16;                // elements are bf16 (both operands of a GEMM must agree); 0 = fp32 read as tf32
+  // hi/lo operand pair (bf16, 3-term product, see GemmTC::x3): the lo tile is the hi tile's coordinates with
+  // batch = z * zmul + lo_z (A side only) and k + lo_k; all zero = plain operand
+  int zmul, lo_z, lo_k;
 };
 int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,
             long long c_col, long long c_z, const float* bias, long long bias_z, int round_out, cudaStream_t s);

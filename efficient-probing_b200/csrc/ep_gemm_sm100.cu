@@ -27,6 +27,11 @@ struct GemmTC {
   int a_mn, b_mn;                             // operand majors
   int a_swap, b_swap;                         // 0: coords (c0, row/k, z); 1: coords (c0, z, row/k)
   int a_zdiv, b_zdiv;                         // operand batch coordinate = z / zdiv (broadcast over z when huge)
+  // x3 (bf16 only): 3-term product of hi/lo operand pairs.  Every stage holds the hi AND lo tile of both operands
+  // and issues A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, so each operand byte is fetched once (a [hi|lo|hi] x [hi|hi|lo]
+  // concatenation along K would fetch the hi tiles twice).  The lo tile of A sits at batch coordinate + a_lo_z
+  // and K coordinate + a_lo_k of the same tensor map, the lo tile of B at K coordinate + b_lo_k.
+  int x3, a_zmul, a_lo_z, a_lo_k, b_lo_k;
   float* C; const float* bias;
   long long c_row, c_col, c_z, bias_z;        // element strides of C and bias
   int round_tf32;                             // round the stored result to tf32 (it feeds another TF32 GEMM)
@@ -85,7 +90,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = 128u * 128u;                       // 128 rows (or 4 atoms x 32 k-rows) x 128 B
   const uint32_t b_bytes = (uint32_t)g.NT * 128u;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t a_lo_off = a_bytes + b_bytes;                // x3 stage: [A_hi | B_hi | A_lo | B_lo]
+  const uint32_t stage_bytes = (g.x3 ? 2u : 1u) * (a_bytes + b_bytes);
   const uint32_t bar_base = smem_base + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (g.stages + s); };
@@ -106,8 +112,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int gk = g.bf16 ? 2 * kGK : kGK;                      // elements per 128-byte row
+  const int gk = g.bf16 ? 2 * kGK : kGK;                      // elements per 128-byte row = K elements per stage
   const int nk = (g.K + gk - 1) / gk;
+  // MN-major operand tile of a stage: atoms of [gk k-rows x 128 bytes of mn]; UMMA K = 8 (tf32) / 16 (bf16) rows
+  const int mn_elems = gk;                                    // mn elements per 128-byte atom row
+  const int mn_atoms = 128 / mn_elems;                        // atoms covering the 128 rows of the A tile
+  const uint32_t atom_bytes = (uint32_t)gk * 128u;            // 4 KB (tf32) / 8 KB (bf16)
+  const uint32_t mn_adv = g.bf16 ? 2048u : 1024u;             // bytes per UMMA K step along the k-rows
   const int n_ct = (g.J + g.NT - 1) / g.NT, n_rt = (g.I + 127) / 128;
   const int ntiles = n_ct * n_rt * g.Z;
   auto tile_coords = [&](int t, int& i0, int& j0, int& z) {
@@ -122,27 +133,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int i0, j0, z;
         tile_coords(t, i0, j0, z);
-        const int za = z / g.a_zdiv, zb = z / g.b_zdiv;
+        const int za = (z / g.a_zdiv) * g.a_zmul, zb = z / g.b_zdiv;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), stage_bytes);
           const int k0 = kc * gk;
-          if (!g.a_mn) {                                       // [128 rows x one 128-byte row of k]
-            tma_load_3d(dst, &tm_a, full_bar(s), k0, g.a_swap ? za : i0, g.a_swap ? i0 : za);
-          } else {                                             // 4 atoms of [32 k-rows x 32 mn]
-            for (int a = 0; a < 4; ++a)
-              tma_load_3d(dst + (uint32_t)a * 4096u, &tm_a, full_bar(s), i0 + 32 * a, g.a_swap ? za : k0,
-                          g.a_swap ? k0 : za);
-          }
-          const uint32_t bdst = dst + a_bytes;
-          if (!g.b_mn) {                                       // [NT rows x 32 k]
-            tma_load_3d(bdst, &tm_b, full_bar(s), k0, g.b_swap ? zb : j0, g.b_swap ? j0 : zb);
-          } else {
-            for (int a = 0; a < g.NT / 32; ++a)
-              tma_load_3d(bdst + (uint32_t)a * 4096u, &tm_b, full_bar(s), j0 + 32 * a, g.b_swap ? zb : k0,
-                          g.b_swap ? k0 : zb);
-          }
+          auto load_pair = [&](uint32_t d, int ka, int zaa, int kb) {
+            if (!g.a_mn) {                                     // [128 rows x one 128-byte row of k]
+              tma_load_3d(d, &tm_a, full_bar(s), ka, g.a_swap ? zaa : i0, g.a_swap ? i0 : zaa);
+            } else {                                           // mn atoms of [gk k-rows x 128 B of mn]
+              for (int a = 0; a < mn_atoms; ++a)
+                tma_load_3d(d + (uint32_t)a * atom_bytes, &tm_a, full_bar(s), i0 + mn_elems * a, g.a_swap ? zaa : ka,
+                            g.a_swap ? ka : zaa);
+            }
+            const uint32_t bdst = d + a_bytes;
+            if (!g.b_mn) {                                     // [NT rows x one 128-byte row of k]
+              tma_load_3d(bdst, &tm_b, full_bar(s), kb, g.b_swap ? zb : j0, g.b_swap ? j0 : zb);
+            } else {
+              for (int a = 0; a < g.NT / mn_elems; ++a)
+                tma_load_3d(bdst + (uint32_t)a * atom_bytes, &tm_b, full_bar(s), j0 + mn_elems * a, g.b_swap ? zb : kb,
+                            g.b_swap ? kb : zb);
+            }
+          };
+          load_pair(dst, k0, za, k0);
+          if (g.x3) load_pair(dst + a_lo_off, k0 + g.a_lo_k, za + g.a_lo_z, k0 + g.b_lo_k);
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -163,12 +178,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t asm_ = smem_base + (uint32_t)s * stage_bytes, bsm = asm_ + a_bytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                        // UMMA K = 8 fp32
-            const uint64_t ad = g.a_mn ? smem_desc_sw128(asm_ + 1024u * k, 4096, 1024)
+            const uint64_t ad = g.a_mn ? smem_desc_sw128(asm_ + mn_adv * k, atom_bytes, 1024)
                                        : smem_desc_sw128(asm_ + 32u * k, 16, 1024);
-            const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + 1024u * k, 4096, 1024)
+            const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + mn_adv * k, atom_bytes, 1024)
                                        : smem_desc_sw128(bsm + 32u * k, 16, 1024);
-            if (g.bf16) umma_bf16(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
-            else umma_tf32(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+            if (g.x3) {                                        // small terms first, then hi.hi
+              const uint64_t lo_step = (uint64_t)(a_lo_off >> 4);  // descriptor start-address field counts 16 B
+              umma_bf16(acc, ad + lo_step, bd, idesc, (uint32_t)((kc | k) != 0));
+              umma_bf16(acc, ad, bd + lo_step, idesc, 1u);
+              umma_bf16(acc, ad, bd, idesc, 1u);
+            } else if (g.bf16) {
+              umma_bf16(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+            } else {
+              umma_tf32(acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+            }
           }
           umma_commit(empty_bar(s));
           if (++s == g.stages) { s = 0; ph ^= 1u; }
@@ -297,9 +320,11 @@ bool gemm_tc_available() { return encode_fn() != nullptr; }
 int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s);
 
 int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, int Z, cudaStream_t s) {
-  g.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (190 * 1024) / (128 * 128 + (size_t)g.NT * 128)));
-  const size_t smem = (size_t)g.stages * (128 * 128 + (size_t)g.NT * 128) + 1024 + 256;
-  EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const size_t per_stage = (g.x3 ? 2 : 1) * (128 * 128 + (size_t)g.NT * 128);
+  g.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (g.x3 ? 216 * 1024 : 190 * 1024) / per_stage));
+  const size_t smem = (size_t)g.stages * per_stage + 1024 + 256;
+  if (smem > 224 * 1024) return EP_ERR_UNSUPPORTED;
+  EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   g.Z = Z;
   const int ntiles = ((g.J + g.NT - 1) / g.NT) * ((g.I + 127) / 128) * Z;
   gemm_tf32_kernel<<<std::min(ntiles, kNumSMs), 384, smem, s>>>(tm_a, tm_b, g);
@@ -308,8 +333,8 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, i
 }
 
 static int side_tmap(CUtensorMap* m, const TcSide& sd, int tile_rows) {
-  // K-major: box = 32 k x tile_rows rows; MN-major: box = 32 mn x 32 k-rows
-  const uint32_t r = sd.mn_major ? 32u : (uint32_t)tile_rows;
+  // K-major: box = one 128-byte row of k x tile_rows rows; MN-major: box = 128 bytes of mn x (32 | 64) k-rows
+  const uint32_t r = sd.mn_major ? (sd.bf16 ? 64u : 32u) : (uint32_t)tile_rows;
   return make_tmap_f32(m, sd.base, sd.d0, sd.d1, sd.d2, sd.s1, sd.s2, sd.swap ? 1u : r, sd.swap ? r : 1u, sd.bf16);
 }
 
@@ -324,7 +349,7 @@ int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int
   g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
   g.epi_mode = 1; g.hl = (__nv_bfloat16*)hl; g.Jrows = Jrows; g.debug = g_debug;
-  g.bf16 = A.bf16;
+  g.bf16 = A.bf16; g.a_zmul = 1;
   return launch_gemm_tc(ta, tb, g, Z, s);
 }
 
@@ -341,6 +366,11 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
   g.C = C; g.bias = bias; g.c_row = c_row; g.c_col = c_col; g.c_z = c_z; g.bias_z = bias_z;
   g.round_tf32 = round_out;
   g.bf16 = A.bf16;
+  g.a_zmul = 1;
+  if (A.lo_k || A.lo_z || B.lo_k) {                            // hi/lo operand pairs: 3-term product
+    if (!A.bf16 || !B.bf16) return EP_ERR_UNSUPPORTED;
+    g.x3 = 1; g.a_zmul = A.zmul > 0 ? A.zmul : 1; g.a_lo_z = A.lo_z; g.a_lo_k = A.lo_k; g.b_lo_k = B.lo_k;
+  }
   return launch_gemm_tc(ta, tb, g, Z, s);
 }
 

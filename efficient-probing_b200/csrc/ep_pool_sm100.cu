@@ -53,7 +53,7 @@ struct KPParams {
   int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, debug, round_out;
   const uint8_t* blocks; // operand blocks [B][nkb][J x 64 tokens]: exp(S - rowmax) (mode 0) or dS (mode 1)
   const float* rsum;     // mode 0
-  float* out;            // mode 0: P (B, M, D); mode 1: partial dq (gridDim.x, M, D)
+  float* out;            // mode 0: P (B, M, D) fp32, or bf16 hi/lo rows (B, M, 2, D) when round_out; mode 1: partial dq
 };
 
 constexpr int kEpiWarps = 8;       // warps 4..11: two per TMEM lane quadrant
@@ -371,8 +371,15 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
             float v = __uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1]);
             if (kMode == 0) {
               v *= __shfl_sync(0xffffffffu, invl[m >> 5], m & 31);
-              if (p.round_out) v = round_tf32(v);
-              if (!(p.debug & 2)) p.out[((size_t)b * p.M + m) * p.D + d] = v;
+              if (p.round_out) {                             // P as bf16 hi/lo rows (b, m, {hi, lo}, d): same bytes as fp32
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
+                pr[0] = hi;
+                pr[p.D] = lo;
+              } else if (!(p.debug & 2)) {
+                p.out[((size_t)b * p.M + m) * p.D + d] = v;
+              }
             } else {
               p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
             }

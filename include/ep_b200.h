@@ -65,6 +65,13 @@ int ep_timing_reset(void);
 /* Which family ep_fwd/ep_bwd would use for this shape under the current mode (0 = none: forced tcgen05
  * but unsupported). */
 int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M);
+/* Layout of the saved pooled-token buffer P that ep_fwd writes and ep_bwd / ep_bwd_proj read back, for this
+ * shape under the current kernel and GEMM modes (which must not change between a forward and its backward):
+ *   0: fp32 (B, M, D);
+ *   1: bf16 pairs (B, M, 2, D) -- row 0 = bf16(P), row 1 = bf16(P - row 0) -- the same number of bytes, read in
+ *      place as the [hi | lo | hi] operand of the tcgen05 projection and weight-gradient GEMMs.
+ * Callers only need this to inspect P; the buffer is always B*M*D*4 bytes.  < 0: EP_ERR_SHAPE. */
+int ep_pooled_layout(int x_dtype, int B, int N, int D, int M, int d_out);
 /* Number of kernels this library has launched in this process (host-side count; launches replayed by a
  * CUDA graph are not seen here -- count the captured step once and multiply). */
 unsigned long long ep_launch_count(void);
