@@ -162,7 +162,7 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
     // whose first and last thirds are the hi/lo pair)
     void* w3f = (char*)workspace + w.w_t;
     StageTimer tm(s);
-    if ((rc = launch_split3(v_w, w3f, Dp, D, D, 1, 1, s))) return rc;
+    if ((rc = launch_split3(v_w, w3f, Dp, D, D, D, 1, 1, s))) return rc;
     tm.mark("proj split3 W");
     const unsigned long long D3 = 3ull * D;
     TcSide A{P, (unsigned long long)D, 2ull * M, (unsigned long long)B, (unsigned long long)D, 2ull * M * D, TC_KMAJOR, 1, 1,
@@ -204,7 +204,7 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
       // tcgen05 3-term bf16 GEMM: rows d, cols j, contraction over b.  A = P's hi/lo rows in place, MN-major
       // (channels contiguous); B = g^T as [g_hi | g_hi | g_lo] (K-major copy, 6*B*D' bytes)
       void* g3t = (char*)workspace + w.g_t;
-      if ((rc = launch_split3_transpose(g_out, g3t, B, Dp, 1, 0, 0, 1, 1, s))) return rc;     // [Dp][3B]
+      if ((rc = launch_split3_transpose(g_out, g3t, B, B, Dp, 1, 0, 0, 1, 1, s))) return rc;     // [Dp][3B]
       tm.mark("dW split3t g");
       const unsigned long long B3 = 3ull * B;
       TcSide A{P, (unsigned long long)D, 2ull * M, (unsigned long long)B, (unsigned long long)D, 2ull * M * D, TC_MNMAJOR, 1,
@@ -222,8 +222,8 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
       float* g3 = (float*)((char*)workspace + w.g_r);              // [(b, m)][3c]  = [big | small | big]
       float* w3 = (float*)((char*)workspace + w.w_t);              // [m][d][3c]    = [big | big | small]
       const int bf = kSplitBf16 && c % 8 == 0;               // bf16 rows need 16-byte strides: 3c * 2 B
-      if ((rc = launch_split3(g_out, g3, (long long)B * M, c, c, 0, bf, s))) return rc;
-      if ((rc = launch_split3_transpose(v_w, w3, c, D, M, (long long)c * D, (long long)3 * c * D, 1, bf, s))) return rc;
+      if ((rc = launch_split3(g_out, g3, (long long)B * M, c, c, c, 0, bf, s))) return rc;
+      if ((rc = launch_split3_transpose(v_w, w3, c, c, D, M, (long long)c * D, (long long)3 * c * D, 1, bf, s))) return rc;
       tm.mark("split3 g, W");
       const unsigned long long c3 = 3ull * c;
       TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1, bf};
@@ -322,19 +322,22 @@ extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_to
                      (cudaStream_t)stream);
 }
 
+static size_t pad64(int v) { return ((size_t)v + 63) / 64 * 64; }
 extern "C" size_t ep_linear_workspace_bytes(int B, int F, int K) {
   if (B <= 0 || F <= 0 || K <= 0) return 0;
-  return 2 * align_up((size_t)3 * K * F * 4, 256) + align_up((size_t)3 * B * F * 4, 256) +
-         align_up((size_t)3 * B * K * 4, 256);
+  const size_t Fp = pad64(F), Kp = pad64(K);                  // operand-copy thirds are padded to the GEMM's K step
+  return align_up(3 * K * Fp * 4, 256) + align_up(3 * F * Kp * 4, 256) + align_up(3 * B * Fp * 4, 256) +
+         align_up(3 * B * Kp * 4, 256);
 }
 namespace {
 struct LinWs { float *w_r, *w_t, *y_r, *d_r; };
 bool lin_ws(void* ws, size_t bytes, int B, int F, int K, LinWs* o) {
   if (!ws || bytes < ep_linear_workspace_bytes(B, F, K)) return false;
   char* p = (char*)ws;
-  o->w_r = (float*)p; p += align_up((size_t)3 * K * F * 4, 256);
-  o->w_t = (float*)p; p += align_up((size_t)3 * K * F * 4, 256);
-  o->y_r = (float*)p; p += align_up((size_t)3 * B * F * 4, 256);
+  const size_t Fp = pad64(F), Kp = pad64(K);
+  o->w_r = (float*)p; p += align_up(3 * K * Fp * 4, 256);
+  o->w_t = (float*)p; p += align_up(3 * F * Kp * 4, 256);
+  o->y_r = (float*)p; p += align_up(3 * B * Fp * 4, 256);
   o->d_r = (float*)p;
   return true;
 }
@@ -349,14 +352,17 @@ extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int
   if (use_tc() && F % 4 == 0 && K % 4 == 0 && lin_ws(workspace, workspace_bytes, B, F, K, &lw)) {
     int rc;                                                     // 3xTF32: y' = [big|small|big], W' = [big|big|small]
     StageTimer tm(s);
+    // bf16 hi/lo copies [hi|lo|hi] x [hi|hi|lo] with thirds padded to the K step: the GEMM loads the hi and lo
+    // thirds of each operand once per stage and issues the three products itself (GemmTC::x3)
     const int bf = kSplitBf16 && F % 8 == 0;
-    if ((rc = launch_split3(W, lw.w_r, K, F, F, 1, bf, s))) return rc;
-    if ((rc = launch_split3(y, lw.y_r, B, F, F, 0, bf, s))) return rc;
+    const int Fp = bf ? (int)pad64(F) : F;
+    if ((rc = launch_split3(W, lw.w_r, K, F, Fp, F, 1, bf, s))) return rc;
+    if ((rc = launch_split3(y, lw.y_r, B, F, Fp, F, 0, bf, s))) return rc;
     tm.mark("lin split3 W,y");
-    const unsigned long long F3 = 3ull * F;
-    TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1, bf};
-    TcSide Bm{lw.w_r, F3, (unsigned long long)K, 1ull, F3, F3 * K, TC_KMAJOR, 0, 1, bf};
-    rc = tc_gemm(A, Bm, B, K, 3 * F, 1, lin_nt(B, K), logits, K, 1, 0, b, 0, 0, s);
+    const unsigned long long F3 = 3ull * Fp;
+    TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1, bf, 1, 0, bf ? Fp : 0};
+    TcSide Bm{lw.w_r, F3, (unsigned long long)K, 1ull, F3, F3 * K, TC_KMAJOR, 0, 1, bf, 0, 0, bf ? 2 * Fp : 0};
+    rc = tc_gemm(A, Bm, B, K, bf ? Fp : 3 * F, 1, lin_nt(B, K), logits, K, 1, 0, b, 0, 0, s);
     tm.mark("lin logits gemm");
     return rc;
   }
@@ -396,13 +402,14 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
     if (!W) return EP_ERR_NULL;
     if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05, 3xTF32, transposed weight copy
       const int bf = kSplitBf16 && K % 8 == 0;
-      if ((rc = launch_split3(dlogits, lw.d_r, B, K, K, 0, bf, s))) return rc;            // [b][3K]
-      if ((rc = launch_split3_transpose(W, lw.w_t, K, F, 1, 0, 0, 1, bf, s))) return rc;  // [f][3K]
+      const int Kp = bf ? (int)pad64(K) : K;
+      if ((rc = launch_split3(dlogits, lw.d_r, B, K, Kp, K, 0, bf, s))) return rc;                // [b][3Kp]
+      if ((rc = launch_split3_transpose(W, lw.w_t, K, Kp, F, 1, 0, 0, 1, bf, s))) return rc;      // [f][3Kp]
       tm.mark("lin split3 dl,Wt");
-      const unsigned long long K3 = 3ull * K;
-      TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1, bf};
-      TcSide Bm{lw.w_t, K3, (unsigned long long)F, 1ull, K3, K3 * F, TC_KMAJOR, 0, 1, bf};
-      if ((rc = tc_gemm(A, Bm, B, F, 3 * K, 1, lin_nt(B, F), dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
+      const unsigned long long K3 = 3ull * Kp;
+      TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1, bf, 1, 0, bf ? Kp : 0};
+      TcSide Bm{lw.w_t, K3, (unsigned long long)F, 1ull, K3, K3 * F, TC_KMAJOR, 0, 1, bf, 0, 0, bf ? 2 * Kp : 0};
+      if ((rc = tc_gemm(A, Bm, B, F, bf ? Kp : 3 * K, 1, lin_nt(B, F), dy, F, 1, 0, nullptr, 0, 0, s))) return rc;
       tm.mark("lin dy gemm");
     } else {
       GemmDesc g{};

@@ -130,9 +130,9 @@ int launch_gemm_tn(const float* A, const float* B, float* C, int I, int J, int K
                    long long ldc, long long a_z, long long b_z, long long c_z, cudaStream_t s);
 bool gemm_tn_ok(int I, int J, long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z);
 // 3-term split copies for the tcgen05 GEMMs; bf16 != 0: dst is bf16 (hi/lo split), else fp32 (tf32 big/small)
-int launch_split3(const float* src, void* dst, long long R, int K, long long ld, int kind, int bf16, cudaStream_t s);
-int launch_split3_transpose(const float* src, void* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
-                            int bf16, cudaStream_t s);
+int launch_split3(const float* src, void* dst, long long R, int K, int Kp, long long ld, int kind, int bf16, cudaStream_t s);
+int launch_split3_transpose(const float* src, void* dst, int K, int Kp, int R, int Z, long long src_z, long long dst_z,
+                            int kind, int bf16, cudaStream_t s);
 int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias, int I, int J, int K, int Z,
                     long long lda, long long ldb, long long ldc, long long a_z, long long b_z, long long c_z,
                     long long bias_z, cudaStream_t s);

@@ -288,6 +288,7 @@ template <> struct Split3<__nv_bfloat16> {              // bf16 hi / lo
     small = __float2bfloat16_rn(x - __bfloat162float(big));
   }
 };
+// (K here is the segment stride: the copies may pad each third to a multiple of the GEMM's K step)
 template <typename T>
 __device__ __forceinline__ void split3_store(T* drow, int K, int k, float x, int kind) {
   T big, small;
@@ -297,29 +298,30 @@ __device__ __forceinline__ void split3_store(T* drow, int K, int k, float x, int
   drow[2 * K + k] = kind == 0 ? big : small;
 }
 
-// src [R x K] (row stride ld) -> dst [R x 3K]
+// src [R x K] (row stride ld) -> dst [R x 3Kp], each third zero-padded from K to Kp columns
 template <typename T>
-__global__ void split3_kernel(const float* __restrict__ src, T* __restrict__ dst, long long R, int K, long long ld,
+__global__ void split3_kernel(const float* __restrict__ src, T* __restrict__ dst, long long R, int K, int Kp, long long ld,
                               int kind) {
-  const long long total = R * K;
+  const long long total = R * Kp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / K;
-    const int k = (int)(i - r * K);
-    split3_store<T>(dst + r * 3 * K, K, k, __ldg(src + r * ld + k), kind);
+    const long long r = i / Kp;
+    const int k = (int)(i - r * Kp);
+    split3_store<T>(dst + r * 3 * Kp, Kp, k, k < K ? __ldg(src + r * ld + k) : 0.f, kind);
   }
 }
-int launch_split3(const float* src, void* dst, long long R, int K, long long ld, int kind, int bf16, cudaStream_t s) {
-  const long long total = R * K;
+int launch_split3(const float* src, void* dst, long long R, int K, int Kp, long long ld, int kind, int bf16,
+                  cudaStream_t s) {
+  const long long total = R * Kp;
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 8 * kNumSMs);
-  if (bf16) split3_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, (__nv_bfloat16*)dst, R, K, ld, kind);
-  else split3_kernel<float><<<grid, 256, 0, s>>>(src, (float*)dst, R, K, ld, kind);
+  if (bf16) split3_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, (__nv_bfloat16*)dst, R, K, Kp, ld, kind);
+  else split3_kernel<float><<<grid, 256, 0, s>>>(src, (float*)dst, R, K, Kp, ld, kind);
   EP_LAUNCH_CHECK();
   return 0;
 }
 
-// src[z] is [K x R] (K rows, row stride R); dst[z] is [R x 3K]  (the transposed, K-major copy)
+// src[z] is [K x R] (K rows, row stride R); dst[z] is [R x 3Kp]  (the transposed, K-major copy, thirds padded to Kp)
 template <typename T>
-__global__ void split3_transpose_kernel(const float* __restrict__ src, T* __restrict__ dst, int K, int R,
+__global__ void split3_transpose_kernel(const float* __restrict__ src, T* __restrict__ dst, int K, int Kp, int R,
                                         long long src_z, long long dst_z, int kind) {
   __shared__ float tile[32][33];
   const float* sp = src + (long long)blockIdx.z * src_z;
@@ -332,14 +334,14 @@ __global__ void split3_transpose_kernel(const float* __restrict__ src, T* __rest
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, k = k0 + threadIdx.x;
-    if (r < R && k < K) split3_store<T>(dp + (long long)r * 3 * K, K, k, tile[threadIdx.x][i], kind);
+    if (r < R && k < Kp) split3_store<T>(dp + (long long)r * 3 * Kp, Kp, k, tile[threadIdx.x][i], kind);   // pad = 0
   }
 }
-int launch_split3_transpose(const float* src, void* dst, int K, int R, int Z, long long src_z, long long dst_z, int kind,
-                            int bf16, cudaStream_t s) {
-  const dim3 grid((R + 31) / 32, (K + 31) / 32, Z), blk(32, 8);
-  if (bf16) split3_transpose_kernel<__nv_bfloat16><<<grid, blk, 0, s>>>(src, (__nv_bfloat16*)dst, K, R, src_z, dst_z, kind);
-  else split3_transpose_kernel<float><<<grid, blk, 0, s>>>(src, (float*)dst, K, R, src_z, dst_z, kind);
+int launch_split3_transpose(const float* src, void* dst, int K, int Kp, int R, int Z, long long src_z, long long dst_z,
+                            int kind, int bf16, cudaStream_t s) {
+  const dim3 grid((R + 31) / 32, (Kp + 31) / 32, Z), blk(32, 8);
+  if (bf16) split3_transpose_kernel<__nv_bfloat16><<<grid, blk, 0, s>>>(src, (__nv_bfloat16*)dst, K, Kp, R, src_z, dst_z, kind);
+  else split3_transpose_kernel<float><<<grid, blk, 0, s>>>(src, (float*)dst, K, Kp, R, src_z, dst_z, kind);
   EP_LAUNCH_CHECK();
   return 0;
 }
