@@ -36,6 +36,10 @@ _SIGNATURES = {
                [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ep_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float] + [c_int] * 5 +
                [c_void_p] * 7 + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "ep_fwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float] + [c_int] * 5 +
+                  [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "ep_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float] + [c_int] * 5 +
+                  [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_void_p] * 4 + [c_void_p, c_size_t, c_void_p]),
     "ep_bwd_proj": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ep_bwd_pool": (c_int, [c_void_p, c_int, c_void_p, c_float] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_void_p,
                                                                                    c_void_p, c_size_t, c_void_p]),

@@ -135,24 +135,26 @@ extern "C" int ep_pooled_layout(int x_dtype, int B, int N, int D, int M, int d_o
   return p_hilo(x_dtype, B, N, D, M, d_out) ? 1 : 0;
 }
 
-extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
-                      float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
-                      float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+namespace {
+// general = 1: the general kernel family with fp32 P whatever the mode (ep_fwd_ex)
+int fwd_impl(const void* x, int x_dtype, const float* cls_token, int cls_batched, int general, const float* v_w,
+             const float* v_b, float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
+             float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
   if (!v_w || !out || !S || !rowmax || !rowsum || !P) return EP_ERR_NULL;
   const Ws w = carve(B, N, D, M);
   if (w.total > 0 && (!workspace || workspace_bytes < w.total)) return EP_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  const int round_p = p_hilo(x_dtype, B, N, D, M, d_out) ? 1 : 0;   // P as bf16 hi/lo rows (see p_hilo)
-  if (use_sm100(x_dtype, B, N, D, M, &rc)) {
+  const int round_p = !general && p_hilo(x_dtype, B, N, D, M, d_out) ? 1 : 0;   // P as bf16 hi/lo rows (see p_hilo)
+  if (!general && use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
     rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p,
                         (char*)workspace + w.sm100, s);
   } else {
     if (rc) return rc;
     t_last_family = 1;
-    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p, s);
+    rc = pool_fwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p, s, cls_batched);
   }
   if (rc) return rc;
   // out[b, m*c + j] = v_w[m*c + j, :] . P[b, m, :] (+ v_b)     -- batched over the M queries
@@ -182,10 +184,41 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
   g.c_i = Dp; g.c_j = 1; g.c_z = c; g.bias_z = c;
   return launch_gemm_v0(g, s);
 }
+}  // namespace
 
+extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
+                      float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
+                      float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+  return fwd_impl(x, x_dtype, cls_token, 0, 0, v_w, v_b, scale, B, N, D, M, d_out, out, S, rowmax, rowsum, P, attn,
+                  workspace, workspace_bytes, stream);
+}
+
+extern "C" int ep_fwd_ex(const void* x, int x_dtype, const float* cls_token, int cls_batched, const float* v_w,
+                         const float* v_b, float scale, int B, int N, int D, int M, int d_out, float* out, float* S,
+                         float* rowmax, float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return fwd_impl(x, x_dtype, cls_token, cls_batched ? 1 : 0, 1, v_w, v_b, scale, B, N, D, M, d_out, out, S, rowmax,
+                  rowsum, P, attn, workspace, workspace_bytes, stream);
+}
+
+namespace {
+int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_dp, const float* out, const float* v_w,
+                  const float* v_b, int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
+                  void* workspace, size_t workspace_bytes, void* stream);
+}
 extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out, const float* v_w, const float* v_b,
                            int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
                            void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_proj_impl(g_out, P, -1, 0, out, v_w, v_b, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace,
+                       workspace_bytes, stream);
+}
+
+namespace {
+// p_layout: -1 = what ep_fwd produces for this shape and mode, else 0 (fp32) / 1 (bf16 hi/lo rows);
+// general_dp = 1: dP is written as fp32 (B, M, D) for the general pooling kernels whatever the family
+int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_dp, const float* out, const float* v_w,
+                  const float* v_b, int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
+                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!g_out || !P || !out || !v_w || !d_v_w) return EP_ERR_NULL;
   if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
   const Ws w = carve(B, N, D, M);
@@ -198,9 +231,11 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
   StageTimer tm(s);
   // delta[b, m] = sum_n A dA = dP[b, m] . P[b, m] = g[b, m, :] . (out[b, m, :] - bias[m, :])
   if ((rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
+  const bool hilo = p_layout < 0 ? p_hilo(x_dtype, B, N, D, M, d_out) : p_layout == 1;
+  if (hilo && !(use_tc() && c % 8 == 0 && B % 64 == 0 && D % 64 == 0)) return EP_ERR_UNSUPPORTED;   // mode changed since ep_fwd
   if (use_tc() && c % 4 == 0) {
     // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch
-    if (p_hilo(x_dtype, B, N, D, M, d_out)) {
+    if (hilo) {
       // tcgen05 3-term bf16 GEMM: rows d, cols j, contraction over b.  A = P's hi/lo rows in place, MN-major
       // (channels contiguous); B = g^T as [g_hi | g_hi | g_lo] (K-major copy, 6*B*D' bytes)
       void* g3t = (char*)workspace + w.g_t;
@@ -229,7 +264,7 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
       TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1, bf};
       TcSide Bm{w3, c3, (unsigned long long)D, (unsigned long long)M, c3, c3 * D, TC_KMAJOR, 0, 1, bf};
       int fam_rc = 0;
-      if (use_sm100(x_dtype, B, N, D, M, &fam_rc)) {
+      if (!general_dp && use_sm100(x_dtype, B, N, D, M, &fam_rc)) {
         // tcgen05 pooling kernels follow: the GEMM epilogue emits what they consume -- dP as bf16 hi/lo operand
         // rows -- and fp32 dP is never written
         void* sm = (char*)workspace + w.sm100;
@@ -240,7 +275,7 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
         tm.mark("dP tc-gemm+hl");
         return 0;
       }
-      if (fam_rc) return fam_rc;
+      if (fam_rc && !general_dp) return fam_rc;
       if ((rc = tc_gemm(A, Bm, B, D, 3 * c, M, round_nt(D), dP, (long long)M * D, 1, D, nullptr, 0, 0, s))) return rc;
       tm.mark("dP tc-gemm");
     }
@@ -266,6 +301,27 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
     if ((rc = launch_gemm_v0(g, s))) return rc;
   }
   return 0;
+}
+}  // namespace
+
+extern "C" int ep_bwd_ex(const void* x, int x_dtype, const float* cls_token, int cls_batched, const float* v_w,
+                         float scale, int B, int N, int D, int M, int d_out, const float* S, const float* rowmax,
+                         const float* rowsum, const float* P, int p_layout, const float* out, const float* v_b,
+                         const float* g_out, float* d_cls_token, float* d_v_w, float* d_v_b, void* dx,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
+  if (rc) return rc;
+  if (!v_w || !S || !rowmax || !rowsum || !P || !out || !g_out || !d_cls_token || !d_v_w) return EP_ERR_NULL;
+  if (p_layout != 0 && p_layout != 1) return EP_ERR_SHAPE;
+  if (M > 64) return EP_ERR_UNSUPPORTED;
+  if ((rc = bwd_proj_impl(g_out, P, p_layout, 1, out, v_w, v_b, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace,
+                          workspace_bytes, stream)))
+    return rc;
+  const Ws w = carve(B, N, D, M);
+  t_last_family = 1;
+  return pool_bwd_v0(x, x_dtype, cls_token, scale, B, N, D, M, rowmax, rowsum, (const float*)((char*)workspace + w.dP),
+                     (const float*)((char*)workspace + w.delta), (float*)((char*)workspace + w.slots), kDqSlots,
+                     d_cls_token, (cudaStream_t)stream, cls_batched ? 1 : 0, dx);
 }
 
 extern "C" int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M,

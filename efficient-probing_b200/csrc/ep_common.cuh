@@ -141,10 +141,11 @@ int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias,
 int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, void* hl, int Jrows, cudaStream_t s);
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
-                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s);
+                float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s,
+                int cls_batched = 0);
 int pool_bwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 const float* rowmax, const float* rowsum, const float* dP, const float* delta,
-                float* dq_slots, int n_slots, float* d_cls, cudaStream_t s);
+                float* dq_slots, int n_slots, float* d_cls, cudaStream_t s, int cls_batched = 0, void* dx = nullptr);
 size_t pool_v0_smem_bytes(int N, int M);
 constexpr int kDqSlots = 16;
 

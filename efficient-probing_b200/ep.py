@@ -17,12 +17,15 @@ def _workspace(x, nbytes):
 
 
 class EPPoolFunction(torch.autograd.Function):
-    """out = EP(x; cls_token, v.weight, v.bias).  Saves x (no copy), the softmax row statistics and the
-    pooled tokens P; backward returns gradients for cls_token, v.weight and v.bias (none for x: the
-    probe trains on a frozen backbone, main_linprobe.py:393-400)."""
+    """out = EP(x; cls_token, v.weight, v.bias).  Saves x (no copy), the logits, the softmax row statistics and
+    the pooled tokens P; backward returns gradients for cls_token, v.weight and v.bias through ``ep_bwd``.
+    The probe trains on a frozen backbone (main_linprobe.py:393-400), so dL/dx is only computed when x
+    requires grad (``--finetuning``), and per-sample queries (``cls_batched``: cls_token is (B, M, D), the
+    ``cls=`` argument of ep.py:32-33) are supported the same way: both go through ``ep_fwd_ex`` /
+    ``ep_bwd_ex`` on the general kernel family."""
 
     @staticmethod
-    def forward(ctx, x, cls_token, v_weight, v_bias, scale, num_queries, d_out, return_attn):
+    def forward(ctx, x, cls_token, v_weight, v_bias, scale, num_queries, d_out, return_attn, cls_batched=False):
         lib = _lib.load()
         _lib.require_cuda(x, "x")
         if x.dim() != 3:
@@ -30,8 +33,9 @@ class EPPoolFunction(torch.autograd.Function):
         x = x.contiguous()
         B, N, D = x.shape
         M = int(num_queries)
-        if cls_token.shape != (1, M, D):
-            raise ValueError(f"cls_token must be (1, {M}, {D}), got {tuple(cls_token.shape)}")
+        want = (B, M, D) if cls_batched else (1, M, D)
+        if tuple(cls_token.shape) != want:
+            raise ValueError(f"cls_token must be {want}, got {tuple(cls_token.shape)}")
         cls32 = cls_token.detach().float().contiguous()
         w32 = v_weight.detach().float().contiguous()
         b32 = None if v_bias is None else v_bias.detach().float().contiguous()
@@ -45,15 +49,24 @@ class EPPoolFunction(torch.autograd.Function):
         attn = torch.empty(B, M, N, dtype=torch.float32, device=dev) if return_attn else None
         nbytes = lib.ep_workspace_bytes(B, N, D, M, d_out)
         ws = _workspace(x, nbytes)
+        xt = _lib.x_dtype_code(x)
         with torch.cuda.device(dev):
-            rc = lib.ep_fwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), _lib.ptr(b32),
-                            float(scale), B, N, D, M, int(d_out), out.data_ptr(), S.data_ptr(), rowmax.data_ptr(),
-                            rowsum.data_ptr(), P.data_ptr(), _lib.ptr(attn), ws.data_ptr(), ws.numel(),
-                            _lib.stream_ptr(dev))
-        _lib.check(rc, "ep_fwd")
+            if cls_batched:
+                rc = lib.ep_fwd_ex(x.data_ptr(), xt, cls32.data_ptr(), 1, w32.data_ptr(), _lib.ptr(b32),
+                                   float(scale), B, N, D, M, int(d_out), out.data_ptr(), S.data_ptr(),
+                                   rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(), _lib.ptr(attn), ws.data_ptr(),
+                                   ws.numel(), _lib.stream_ptr(dev))
+                p_layout = 0
+            else:
+                p_layout = lib.ep_pooled_layout(xt, B, N, D, M, int(d_out))      # as ep_fwd will write it
+                rc = lib.ep_fwd(x.data_ptr(), xt, cls32.data_ptr(), w32.data_ptr(), _lib.ptr(b32),
+                                float(scale), B, N, D, M, int(d_out), out.data_ptr(), S.data_ptr(), rowmax.data_ptr(),
+                                rowsum.data_ptr(), P.data_ptr(), _lib.ptr(attn), ws.data_ptr(), ws.numel(),
+                                _lib.stream_ptr(dev))
+        _lib.check(rc, "ep_fwd_ex" if cls_batched else "ep_fwd")
         ctx.save_for_backward(x, cls32, w32, S, rowmax, rowsum, P, out, b32)
         ctx.meta = (float(scale), M, int(d_out), v_bias is not None, cls_token.dtype, v_weight.dtype)
-        ctx.x_needs_grad = x.requires_grad
+        ctx.ext = (bool(cls_batched), int(p_layout))
         if return_attn:
             ctx.mark_non_differentiable(attn)
             return out, attn
@@ -61,27 +74,34 @@ class EPPoolFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, *unused):
-        if ctx.x_needs_grad and ctx.needs_input_grad[0]:
-            raise NotImplementedError("dL/dx is not produced: the EP probe trains on a frozen backbone "
-                                      "(main_linprobe.py:393-400); --finetuning is out of scope")
         lib = _lib.load()
         x, cls32, w32, S, rowmax, rowsum, P, out, b32 = ctx.saved_tensors
         scale, M, d_out, has_bias, cls_dtype, w_dtype = ctx.meta
         B, N, D = x.shape
         dev = x.device
         g = g.detach().float().contiguous()
-        d_cls = torch.empty(1, M, D, dtype=torch.float32, device=dev)
+        cls_batched, p_layout = ctx.ext
+        want_dx = ctx.needs_input_grad[0]
+        d_cls = torch.empty(B if cls_batched else 1, M, D, dtype=torch.float32, device=dev)
         d_w = torch.empty_like(w32)
         d_b = torch.empty(D // d_out, dtype=torch.float32, device=dev) if has_bias else None
         ws = _workspace(x, lib.ep_workspace_bytes(B, N, D, M, d_out))
+        dx = torch.empty_like(x) if want_dx else None
         with torch.cuda.device(dev):
-            rc = lib.ep_bwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), scale,
-                            B, N, D, M, d_out, S.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(),
-                            out.data_ptr(), _lib.ptr(b32), g.data_ptr(),
-                            d_cls.data_ptr(), d_w.data_ptr(), _lib.ptr(d_b), ws.data_ptr(), ws.numel(),
-                            _lib.stream_ptr(dev))
+            if cls_batched or want_dx:
+                rc = lib.ep_bwd_ex(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), int(cls_batched), w32.data_ptr(),
+                                   scale, B, N, D, M, d_out, S.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(),
+                                   P.data_ptr(), p_layout, out.data_ptr(), _lib.ptr(b32), g.data_ptr(),
+                                   d_cls.data_ptr(), d_w.data_ptr(), _lib.ptr(d_b), _lib.ptr(dx), ws.data_ptr(),
+                                   ws.numel(), _lib.stream_ptr(dev))
+            else:
+                rc = lib.ep_bwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), scale,
+                                B, N, D, M, d_out, S.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(),
+                                out.data_ptr(), _lib.ptr(b32), g.data_ptr(),
+                                d_cls.data_ptr(), d_w.data_ptr(), _lib.ptr(d_b), ws.data_ptr(), ws.numel(),
+                                _lib.stream_ptr(dev))
         _lib.check(rc, "ep_bwd")
-        return None, d_cls.to(cls_dtype), d_w.to(w_dtype), d_b, None, None, None, None
+        return dx, d_cls.to(cls_dtype), d_w.to(w_dtype), d_b, None, None, None, None, None
 
 
 class EfficientProbing(nn.Module):
@@ -103,9 +123,6 @@ class EfficientProbing(nn.Module):
         if self.num_heads != 1:
             # the reference forward itself fails for num_heads > 1 (view at ep.py:45)
             raise RuntimeError("EfficientProbing supports num_heads == 1 only (as the reference, ep.py:45)")
-        if cls is not None:
-            raise NotImplementedError("per-sample external queries (cls=...) are not wired: no caller in the "
-                                      "reference passes them (ep.py:32-33)")
         C = x.shape[-1]
         if C % (self.d_out * self.num_queries) != 0:
             raise RuntimeError(f"shape '[{x.shape[0]}, {x.shape[1]}, {self.num_queries}, "
@@ -114,8 +131,13 @@ class EfficientProbing(nn.Module):
 
     def forward(self, x: torch.Tensor, cls=None, **_: Any) -> torch.Tensor:
         self._check(x, cls)
+        if cls is not None:
+            # external per-sample queries replace the learned ones (ep.py:32-33,35: reshaped to (B, M, C))
+            q = cls.reshape(x.shape[0], self.num_queries, x.shape[-1])
+            return EPPoolFunction.apply(x, q, self.v.weight, self.v.bias, self.scale, self.num_queries, self.d_out,
+                                        False, True)
         return EPPoolFunction.apply(x, self.cls_token, self.v.weight, self.v.bias, self.scale,
-                                    self.num_queries, self.d_out, False)
+                                    self.num_queries, self.d_out, False, False)
 
     @torch.no_grad()
     def attention_maps(self, x: torch.Tensor) -> torch.Tensor:

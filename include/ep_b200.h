@@ -94,7 +94,7 @@ int ep_fwd(const void* x, int x_dtype, const float* cls_token, const float* v_w,
  * g_out = dL/d out (B, D/d_out); out = what ep_fwd returned and v_b the bias it used (nullable) -- the
  * softmax-backward row term sum_n A dA equals g . (out - v_b) per query, so no pass over P is needed for it.
  * Writes d_cls_token (M, D), d_v_w (D/d_out, D), d_v_b (D/d_out, nullable).  The frozen-backbone path needs
- * no dL/dx (main_linprobe.py:393-400). */
+ * no dL/dx (main_linprobe.py:393-400; ep_bwd_ex produces it). */
 int ep_bwd(const void* x, int x_dtype, const float* cls_token, const float* v_w, float scale,
            int B, int N, int D, int M, int d_out,
            const float* S, const float* rowmax, const float* rowsum, const float* P, const float* out,
@@ -114,6 +114,25 @@ int ep_bwd_proj(const float* g_out, const float* P, const float* out, const floa
 int ep_bwd_pool(const void* x, int x_dtype, const float* cls_token, float scale, int B, int N, int D, int M, int d_out,
                 const float* S, const float* rowmax, const float* rowsum, float* d_cls_token,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* The rest of EfficientProbing.forward's surface (poolings/ep.py:28-33) and the input gradient, on the general
+ * (CUDA-core) kernel family -- the paths no reference script exercises while probing a frozen backbone:
+ *   cls_batched != 0 : cls_token is (B, M, D), the per-sample external queries of forward(x, cls=...)
+ *                      (ep.py:32-33); d_cls_token is then (B, M, D) as well;
+ *   dx != NULL       : dL/dx (B, N, D) in x's dtype is written too (--finetuning, main_linprobe.py:152-154):
+ *                      dx[b,n] = sum_m  scale * dS[b,m,n] * cls_token[m] + A[b,m,n] * dP[b,m].
+ * ep_fwd_ex always saves P as fp32 (layout 0).  ep_bwd_ex takes the layout of the P it is given: 0 after
+ * ep_fwd_ex, ep_pooled_layout(...) after ep_fwd (so dx is available behind the fast forward as well). */
+int ep_fwd_ex(const void* x, int x_dtype, const float* cls_token, int cls_batched, const float* v_w, const float* v_b,
+              float scale, int B, int N, int D, int M, int d_out,
+              float* out, float* S, float* rowmax, float* rowsum, float* P, float* attn,
+              void* workspace, size_t workspace_bytes, void* stream);
+int ep_bwd_ex(const void* x, int x_dtype, const float* cls_token, int cls_batched, const float* v_w, float scale,
+              int B, int N, int D, int M, int d_out,
+              const float* S, const float* rowmax, const float* rowsum, const float* P, int p_layout,
+              const float* out, const float* v_b, const float* g_out,
+              float* d_cls_token, float* d_v_w, float* d_v_b, void* dx,
+              void* workspace, size_t workspace_bytes, void* stream);
 
 /* tools/ep_attention_maps.py:51-58 for a batch: attn[b] = softmax(scale * cls_token @ x[b]^T), (B, M, N). */
 int ep_attention_maps(const void* x, int x_dtype, const float* cls_token, float scale,

@@ -70,7 +70,7 @@ def test_constructor_attributes_and_errors():
         E.EfficientProbing(64, num_heads=2, num_queries=8)(torch.randn(2, 5, 64))
     with pytest.raises(RuntimeError):                         # 64 % 5 != 0: the reference's reshape error (ep.py:40)
         E.EfficientProbing(64, num_queries=5)(torch.randn(2, 5, 64))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):                         # external queries take the same (CUDA-only) path
         m(torch.randn(2, 5, 64), cls=torch.randn(2, 8, 64))
 
 

@@ -42,7 +42,7 @@ def head_from_params(p: O.EPParams, K):
 
 
 def close(got, ref, tol, what):
-    ref = ref.to(got.device)
+    got, ref = got.detach(), ref.detach().to(got.device)
     err = (got.double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30)
     if ref.double().norm() < 1e-12:                    # identically-zero reference (bias under BatchNorm)
         assert got.double().norm() < 1e-6, what
@@ -191,11 +191,86 @@ def test_errors_are_loud():
         head[0](torch.randn(2, 5, 64, device=DEV, dtype=torch.float16))
     with pytest.raises(ValueError):
         head[0](torch.zeros(2, 5, 72, device=DEV))        # cls_token is (1, 8, 64)
-    x = torch.randn(2, 5, 64, device=DEV, requires_grad=True)
-    out = head[0](x)
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
+    with pytest.raises(RuntimeError):
+        head[0](torch.zeros(2, 5, 64, device=DEV), cls=torch.zeros(2, 4, 64, device=DEV))   # not (B, M, C): ep.py:35
     assert E._lib.load().ep_device_check() == 0
+
+
+DX_CASES = [  # B, N, D, M, d_out, bias, q_gain
+    (4, 257, 1024, 32, 1, False, 25.0),                # config 2 shape (tcgen05 forward, hi/lo P when B % 64 == 0)
+    (64, 70, 256, 8, 1, False, 10.0),                  # B % 64 == 0: P saved as bf16 hi/lo rows by the forward
+    (5, 50, 384, 12, 2, True, 20.0),                   # d_out = 2, bias, M not a power of two
+    (3, 33, 128, 64, 1, False, 10.0),                  # M = 64
+    (2, 19, 72, 6, 1, False, 5.0),                     # M % 4 != 0, D % 128 != 0
+]
+
+
+@pytest.mark.parametrize("case", DX_CASES, ids=lambda c: "B%d_N%d_D%d_M%d_do%d_b%d" % c[:6])
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_input_gradient_vs_oracle(case, xdt):
+    """--finetuning (main_linprobe.py:152-154): dL/dx through the pooling, against the closed form of the
+    oracle and (fp32) against autograd through the reference formulation."""
+    B, N, D, M, d_out, bias, q_gain = case
+    p = O.build_head(D, M, 10, d_out=d_out, qkv_bias=bias, seed=0)
+    p.cls_token = p.cls_token * q_gain
+    x = O.synthetic_tokens(B, N, D, seed=99)
+    g = torch.randn(B, D // d_out, generator=torch.Generator().manual_seed(5))
+    xr = x.double().requires_grad_(True)
+    prm = [t.double().requires_grad_(True) for t in (p.cls_token, p.v_weight)]
+    bref = p.v_bias.double().requires_grad_(True) if bias else None
+    O.ep_forward(xr, prm[0], prm[1], bref, p.scale, M, d_out).backward(g.double())
+    out_p, attn, P, _, _ = O.ep_forward_pooled(x.double(), p.cls_token.double(), p.v_weight.double(),
+                                              p.v_bias.double() if bias else None, p.scale, M, d_out)
+    cf = O.ep_backward_pooled(x.double(), p.cls_token.double(), p.v_weight.double(), p.scale, M, d_out, attn, P,
+                              g.double(), want_dx=True)
+    assert O.rel_err(cf["d_x"], xr.grad) < 1e-10         # the oracle's closed form == autograd of ep.py:28-47
+    pool = E.EfficientProbing(D, num_queries=M, d_out=d_out, qkv_bias=bias).to(DEV)
+    with torch.no_grad():
+        pool.cls_token.copy_(p.cls_token); pool.v.weight.copy_(p.v_weight)
+        if bias:
+            pool.v.bias.copy_(p.v_bias)
+    xg = x.to(DEV, xdt).requires_grad_(True)
+    pool(xg).backward(g.to(DEV))
+    assert xg.grad.dtype == xdt and xg.grad.shape == xg.shape
+    # bf16 tokens get a bf16 gradient: 2^-9 rounding per element on top of the fp32-accumulated value
+    close(xg.grad.float(), xr.grad, 2e-4 if xdt == torch.float32 else 3e-3, "dx")
+    close(pool.cls_token.grad, prm[0].grad, TOL_GRAD, "d cls_token")
+    close(pool.v.weight.grad, prm[1].grad, TOL_GRAD, "d v.weight")
+    if bias:
+        close(pool.v.bias.grad, bref.grad, TOL_GRAD, "d v.bias")
+
+
+@pytest.mark.parametrize("case", DX_CASES[1:], ids=lambda c: "B%d_N%d_D%d_M%d_do%d_b%d" % c[:6])
+def test_external_queries_vs_reference_formulation(case):
+    """forward(x, cls=...) (ep.py:32-33): per-sample queries replace cls_token; gradients flow to them."""
+    B, N, D, M, d_out, bias, q_gain = case
+    p = O.build_head(D, M, 10, d_out=d_out, qkv_bias=bias, seed=0)
+    x = O.synthetic_tokens(B, N, D, seed=7)
+    gen = torch.Generator().manual_seed(11)
+    q = torch.randn(B, M, D, generator=gen) * 0.02 * q_gain
+    g = torch.randn(B, D // d_out, generator=gen)
+    xr, qr = x.double().requires_grad_(True), q.double().requires_grad_(True)
+    wr = p.v_weight.double().requires_grad_(True)
+    bref = p.v_bias.double().requires_grad_(True) if bias else None
+    ref_out = O.ep_forward(xr, qr, wr, bref, p.scale, M, d_out)
+    ref_out.backward(g.double())
+    pool = E.EfficientProbing(D, num_queries=M, d_out=d_out, qkv_bias=bias).to(DEV)
+    with torch.no_grad():
+        pool.v.weight.copy_(p.v_weight)
+        if bias:
+            pool.v.bias.copy_(p.v_bias)
+    for want_dx in (False, True):
+        pool.zero_grad()
+        xg = x.to(DEV).requires_grad_(want_dx)               # bf16 tokens
+        qg = q.to(DEV).requires_grad_(True)
+        out = pool(xg, cls=qg)
+        close(out, ref_out.detach(), TOL_FWD, "out")
+        out.backward(g.to(DEV))
+        close(qg.grad, qr.grad, TOL_GRAD, "d cls (per sample)")
+        close(pool.v.weight.grad, wr.grad, TOL_GRAD, "d v.weight")
+        assert pool.cls_token.grad is None                   # the learned queries are unused, as in the reference
+        if want_dx:
+            close(xg.grad.float(), xr.grad, 3e-3, "dx")
 
 
 def test_host_buffer_step_matches_device_step():
