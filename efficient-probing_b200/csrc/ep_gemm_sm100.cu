@@ -137,11 +137,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
-          if (g.debug & 128) {                                 // developer knob: no loads (MMA-only bound)
-            mbar_arrive(full_bar(s));
-            if (++s == g.stages) { s = 0; ph ^= 1u; }
-            continue;
-          }
           mbar_arrive_expect_tx(full_bar(s), stage_bytes);
           const int k0 = kc * gk;
           auto load_pair = [&](uint32_t d, int ka, int zaa, int kb) {
@@ -187,7 +182,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                        : smem_desc_sw128(asm_ + 32u * k, 16, 1024);
             const uint64_t bd = g.b_mn ? smem_desc_sw128(bsm + mn_adv * k, atom_bytes, 1024)
                                        : smem_desc_sw128(bsm + 32u * k, 16, 1024);
-            if (g.debug & 64) continue;                        // developer knob: no MMAs (load-only bound)
             if (g.x3) {                                        // small terms first, then hi.hi
               const uint64_t lo_step = (uint64_t)(a_lo_off >> 4);  // descriptor start-address field counts 16 B
               umma_bf16(acc, ad + lo_step, bd, idesc, (uint32_t)((kc | k) != 0));

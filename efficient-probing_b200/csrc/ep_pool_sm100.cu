@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "ep_ptx.cuh"
 #include "ep_sm100.cuh"
@@ -41,12 +42,14 @@ constexpr int kSmemBudget = 220 * 1024;
 struct KSParams {
   int B, N, D, M, J, ntiles, G, ngroups, nchunks, nstages, w_batched, nbuf, bufcols, tmem_cols, nkb, ndelta;
   int tail_rows;         // > 0: the last token tile of a sample is loaded as this many rows only (single tile group)
-  float* out;            // mode 0: logits (B, M, N)
-  uint8_t* blocks;       // mode 1: dS as operand blocks [B][nkb][J rows x 64 tokens] bf16 hi/lo, swizzled
+  float* out;            // mode 0, 2: logits (B, M, N)
+  uint8_t* blocks;       // operand blocks [B][nkb][J rows x 64 tokens] bf16 hi/lo, swizzled: dS (mode 1), exp(S - max) (mode 2)
   const float* S;        // mode 1: saved logits
   const float* rmax;     // mode 1
   const float* rsum;     // mode 1
   const float* delta;    // mode 1: ndelta partial sums of delta, each (B, M)
+  float* rmax_out;       // mode 2: softmax row statistics (B, M)
+  float* rsum_out;       // mode 2
 };
 
 struct KPParams {
@@ -80,6 +83,31 @@ __device__ __forceinline__ void store_hilo(uint8_t* blk, int m, int t, float e) 
 // ------------------------------------------------------------------------------------------------
 // logit-type kernel
 // ------------------------------------------------------------------------------------------------
+// 8 values per lane reduced over the 32 lanes of a warp in 9 shuffles: at each of the first three steps a lane
+// hands half of its values to the partner and keeps the other half.  Returns value ((lane >> 2) & 7 in bit order
+// 4,3,2) reduced over all lanes (replicated on 4 lanes).
+template <bool kMax>
+__device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
+  auto op = [](float a, float b) { return kMax ? fmaxf(a, b) : a + b; };
+  const bool u1 = lane & 16, u2 = lane & 8, u3 = lane & 4;
+  float a[4], bq[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    a[i] = op(u1 ? v[i + 4] : v[i], __shfl_xor_sync(0xffffffffu, u1 ? v[i] : v[i + 4], 16));
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    bq[i] = op(u2 ? a[i + 2] : a[i], __shfl_xor_sync(0xffffffffu, u2 ? a[i] : a[i + 2], 8));
+  float c = op(u3 ? bq[1] : bq[0], __shfl_xor_sync(0xffffffffu, u3 ? bq[0] : bq[1], 4));
+  c = op(c, __shfl_xor_sync(0xffffffffu, c, 2));
+  return op(c, __shfl_xor_sync(0xffffffffu, c, 1));
+}
+constexpr int kUB = 3;                                      // mode 2: accumulator units fetched per TMEM wait
+
+// kMode 0: logits S out.  kMode 1: dS operand blocks out (backward).  kMode 2: forward with the softmax fused into
+// the epilogue -- needs the whole sample in one accumulator buffer (ngroups == 1): writes S, rowmax, rowsum and
+// exp(S - rowmax) as the pool-type kernel's operand blocks, so no separate pass over S exists.
+constexpr int kStatBytes = 2 * kEpiWarps * 64 * 4;          // mode 2: per-warp partial max / sum of 64 queries
+
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xt,
@@ -90,7 +118,7 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   // the slack) and only reach accumulator rows n >= N, which the epilogue never uses.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t bar_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_base = bar_base + 1024u;
+  const uint32_t smem_base = bar_base + (kMode == 2 ? 1024u + (uint32_t)kStatBytes : 1024u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_bytes = (uint32_t)p.J * 128u;
   const uint32_t tail_bytes = p.tail_rows ? (uint32_t)p.tail_rows * 128u : (uint32_t)kXChunkBytes;
@@ -198,6 +226,124 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       mbar_wait(tfull_bar(buf), ((uint32_t)(it / p.nbuf)) & 1u);
       tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.bufcols);
+      if constexpr (kMode == 2) {
+        // ---- fused softmax: two passes over the accumulators (TMEM reads are cheap), no atomics -- every warp
+        // reduces into its own row of the partial tables and the rows are combined in a fixed order.  The
+        // epilogue has to finish inside the next sample's streaming time, so TMEM is read four units per wait
+        // and the 8 queries of a unit are reduced over the 32 token lanes with a transposing butterfly
+        // (9 shuffles; lane l ends with query ((l >> 2) & 7)'s value).
+        float* pmax = reinterpret_cast<float*>(smem_raw + (bar_base + 1024u - smem_u32(smem_raw)));   // [8][64]
+        float* psum = pmax + kEpiWarps * 64;                                                          // [8][64]
+        const int ew = warp - 4;
+        const int nunits = gt * upt;
+        const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        pmax[ew * 64 + lane] = -INFINITY;
+        pmax[ew * 64 + 32 + lane] = -INFINITY;
+        __syncwarp();
+        // this warp's units u = eh, eh + 2, ... as (tile, column unit), advanced without divisions
+        const int t_first = eh / upt, j_first = eh - t_first * upt;
+        auto advance = [&](int& t, int& jj) {
+          jj += 2;
+          if (jj >= upt) { jj -= upt; ++t; }
+          if (jj >= upt) { jj -= upt; ++t; }
+        };
+        {
+          int t = t_first, jj = j_first;
+          for (int u0 = eh; u0 < nunits; u0 += 2 * kUB) {
+            uint32_t r[kUB][16];
+            int tk[kUB], jk[kUB];
+#pragma unroll
+            for (int k = 0; k < kUB; ++k) {
+              tk[k] = t; jk[k] = jj << 4;
+              if (u0 + 2 * k < nunits) tmem_ld16(acc + (uint32_t)(t * p.J + (jj << 4)), r[k]);
+              advance(t, jj);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < kUB; ++k) {
+              if (u0 + 2 * k < nunits) {
+                const bool valid = (t0 + tk[k]) * kTileRows + wq * 32 + lane < p.N;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  v[i] = valid ? __uint_as_float(r[k][2 * i]) + __uint_as_float(r[k][2 * i + 1]) : -INFINITY;
+                const float red = reduce8<true>(v, lane);
+                if ((lane & 3) == 0) {
+                  float* slot = pmax + ew * 64 + (jk[k] >> 1) + ridx;
+                  *slot = fmaxf(*slot, red);
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        float mx_lo = -INFINITY, mx_hi = -INFINITY;           // lane l: queries l and 32 + l
+#pragma unroll
+        for (int w = 0; w < kEpiWarps; ++w) {
+          mx_lo = fmaxf(mx_lo, pmax[w * 64 + lane]);
+          mx_hi = fmaxf(mx_hi, pmax[w * 64 + 32 + lane]);
+        }
+        psum[ew * 64 + lane] = 0.f;
+        psum[ew * 64 + 32 + lane] = 0.f;
+        __syncwarp();
+        {
+          int t = t_first, jj = j_first;
+          for (int u0 = eh; u0 < nunits; u0 += 2 * kUB) {
+            uint32_t r[kUB][16];
+            int tk[kUB], jk[kUB];
+#pragma unroll
+            for (int k = 0; k < kUB; ++k) {
+              tk[k] = t; jk[k] = jj << 4;
+              if (u0 + 2 * k < nunits) tmem_ld16(acc + (uint32_t)(t * p.J + (jj << 4)), r[k]);
+              advance(t, jj);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < kUB; ++k) {
+              if (u0 + 2 * k < nunits) {
+                const int j0 = jk[k];
+                const int n = (t0 + tk[k]) * kTileRows + wq * 32 + lane;
+                const bool valid = n < p.N;
+                const int kb = n >> 6, tt = n & 63;
+                uint8_t* blk = kb < p.nkb ? p.blocks + ((size_t)b * p.nkb + kb) * ((size_t)p.J * 128) : nullptr;
+                float* srow = p.out + ((size_t)b * p.M + (j0 >> 1)) * p.N + n;
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int m = (j0 >> 1) + i;                // warp-uniform
+                  const float v = __uint_as_float(r[k][2 * i]) + __uint_as_float(r[k][2 * i + 1]);
+                  const float mx = __shfl_sync(0xffffffffu, m < 32 ? mx_lo : mx_hi, m & 31);
+                  const bool on = valid && m < p.M;
+                  e[i] = on ? __expf(v - mx) : 0.f;           // rows past 2M, tokens past N: zeros
+                  if (on) srow[(size_t)i * p.N] = v;
+                  if (blk) store_hilo(blk, m, tt, e[i]);
+                }
+                const float red = reduce8<false>(e, lane);
+                if ((lane & 3) == 0) psum[ew * 64 + (j0 >> 1) + ridx] += red;
+                __syncwarp();
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(buf));
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (ew == 0) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int m = 32 * h + lane;
+            float su = 0.f;
+#pragma unroll
+            for (int w = 0; w < kEpiWarps; ++w) su += psum[w * 64 + m];
+            if (m < p.M) {
+              p.rmax_out[(size_t)b * p.M + m] = h ? mx_hi : mx_lo;
+              p.rsum_out[(size_t)b * p.M + m] = su;
+            }
+          }
+        }
+        continue;
+      }
       for (int u = eh; u < gt * upt; u += 2) {
         const int t = u / upt, j0 = (u - t * upt) << 4;
         const int n = (t0 + t) * kTileRows + wq * 32 + lane;
@@ -228,10 +374,11 @@ ks_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             // past N and operand rows past 2M are written as zeros so the block needs no memset
             float ds = 0.f;
             if (m < p.M) {
-              const int h = m >> 5, src = m & 31;
-              const float mx = __shfl_sync(0xffffffffu, st_mx[h], src);
-              const float inv = __shfl_sync(0xffffffffu, st_inv[h], src);
-              const float dl = __shfl_sync(0xffffffffu, st_dl[h], src);
+              const bool h = m >= 32;                          // (selects, not indexing: the arrays stay in registers)
+              const int src = m & 31;
+              const float mx = __shfl_sync(0xffffffffu, h ? st_mx[1] : st_mx[0], src);
+              const float inv = __shfl_sync(0xffffffffu, h ? st_inv[1] : st_inv[0], src);
+              const float dl = __shfl_sync(0xffffffffu, h ? st_dl[1] : st_dl[0], src);
               if (n < p.N) ds = __expf(sv[i] - mx) * inv * (v - dl);
             }
             if (blk) store_hilo(blk, m, tt, ds);
@@ -615,7 +762,7 @@ int set_dyn_smem(K kernel, size_t bytes) {
 template <int kMode>
 int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, int M, const Plan& pl, float* out,
               uint8_t* blocks, const float* S, const float* rmax, const float* rsum, const float* delta, int ndelta,
-              cudaStream_t s) {
+              cudaStream_t s, float* rmax_out = nullptr, float* rsum_out = nullptr) {
   CUtensorMap tm_x, tm_xt, tm_w;
   int rc;
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTileRows))) return rc;
@@ -627,9 +774,12 @@ int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, 
   p.bufcols = pl.G * pl.J; p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
   p.nkb = pl.nkb; p.ndelta = ndelta; p.tail_rows = pl.tail_rows;
   p.out = out; p.blocks = blocks; p.S = S; p.rmax = rmax; p.rsum = rsum; p.delta = delta;
-  if ((rc = set_dyn_smem(ks_kernel<kMode>, pl.ks_smem))) return rc;
+  p.rmax_out = rmax_out; p.rsum_out = rsum_out;
+  const size_t smem = pl.ks_smem + (kMode == 2 ? kStatBytes : 0);
+  if (smem > 227 * 1024) return EP_ERR_UNSUPPORTED;
+  if ((rc = set_dyn_smem(ks_kernel<kMode>, smem))) return rc;
   const int grid = std::min(B * pl.ngroups, kNumSMs);
-  ks_kernel<kMode><<<grid, kThreads, pl.ks_smem, s>>>(tm_x, tm_xt, tm_w, p);
+  ks_kernel<kMode><<<grid, kThreads, smem, s>>>(tm_x, tm_xt, tm_w, p);
   EP_LAUNCH_CHECK();
   return 0;
 }
@@ -685,6 +835,14 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
   EP_LAUNCH_CHECK();
   tm.mark("split_q");
+  // the softmax rides in the logit kernel's epilogue when one accumulator buffer holds the whole sample
+  const bool fused = pl.ngroups == 1 && attn == nullptr && P != nullptr && !(g_debug & 512) &&
+                     pl.ks_smem + kStatBytes <= 227 * 1024;
+  if (fused) {
+    if ((rc = launch_ks<2>(x, qhl, 0, B, N, D, M, pl, S, blocks, nullptr, nullptr, nullptr, nullptr, 0, s, rowmax, rowsum)))
+      return rc;
+    tm.mark("ks<2> logits+softmax");
+  } else {
   if ((rc = launch_ks<0>(x, qhl, 0, B, N, D, M, pl, S, nullptr, nullptr, nullptr, nullptr, nullptr, 0, s))) return rc;
   tm.mark("ks<0> logits");
   const long long rows = (long long)B * (pl.J / 2);
@@ -698,6 +856,7 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   }
   EP_LAUNCH_CHECK();
   tm.mark("rowstats");
+  }
   if (P == nullptr) return 0;
   rc = launch_kp<0>(x, B, N, D, M, pl, blocks, rowsum, P, nullptr, round_p, s);
   tm.mark("kp<0> pool");

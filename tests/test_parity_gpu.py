@@ -196,6 +196,32 @@ def test_errors_are_loud():
     assert E._lib.load().ep_device_check() == 0
 
 
+def test_fused_and_separate_softmax_agree():
+    """ep_set_debug(512) splits the forward softmax out of the logit kernel: both paths must give the same
+    pooled output, saved statistics and attention-derived gradients."""
+    lib = E._lib.load()
+    B, N, D, M = 20, 257, 1024, 32
+    p = O.build_head(D, M, 10, seed=0)
+    p.cls_token = p.cls_token * 25.0
+    x = O.synthetic_tokens(B, N, D, seed=3).to(DEV)
+    g = torch.randn(B, D, device=DEV)
+    res = []
+    for flags in (0, 512):
+        lib.ep_set_debug(flags)
+        try:
+            pool = E.EfficientProbing(D, num_queries=M).to(DEV)
+            with torch.no_grad():
+                pool.cls_token.copy_(p.cls_token); pool.v.weight.copy_(p.v_weight)
+            out = pool(x)
+            out.backward(g)
+            res.append((out.detach(), pool.cls_token.grad.clone(), pool.v.weight.grad.clone()))
+        finally:
+            lib.ep_set_debug(0)
+    assert lib.ep_last_kernel_family() == 2
+    for a, b_, what in zip(res[0], res[1], ("out", "d cls_token", "d v.weight")):
+        close(a, b_, 1e-5, what)
+
+
 DX_CASES = [  # B, N, D, M, d_out, bias, q_gain
     (4, 257, 1024, 32, 1, False, 25.0),                # config 2 shape (tcgen05 forward, hi/lo P when B % 64 == 0)
     (64, 70, 256, 8, 1, False, 10.0),                  # B % 64 == 0: P saved as bf16 hi/lo rows by the forward
