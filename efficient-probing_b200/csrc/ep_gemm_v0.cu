@@ -309,8 +309,39 @@ __global__ void split3_kernel(const float* __restrict__ src, T* __restrict__ dst
     split3_store<T>(dst + r * 3 * Kp, Kp, k, k < K ? __ldg(src + r * ld + k) : 0.f, kind);
   }
 }
+// bf16 copies with K, Kp, ld all multiples of 8: 8 elements per thread, 16-byte stores
+__global__ void split3_bf16x8_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long R, int K,
+                                     int Kp, long long ld, int kind) {
+  const int k8 = Kp >> 3;
+  const long long total = R * k8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / k8;
+    const int k = (int)(i - r * k8) << 3;
+    float v[8];
+    if (k < K) load8(src + r * ld + k, v);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Split3<__nv_bfloat16>::split(v[e], hi[e], lo[e]);
+    __nv_bfloat16* drow = dst + r * 3 * Kp + k;
+    *reinterpret_cast<uint4*>(drow) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(drow + Kp) = *reinterpret_cast<const uint4*>(kind == 0 ? lo : hi);
+    *reinterpret_cast<uint4*>(drow + 2 * Kp) = *reinterpret_cast<const uint4*>(kind == 0 ? hi : lo);
+  }
+}
 int launch_split3(const float* src, void* dst, long long R, int K, int Kp, long long ld, int kind, int bf16,
                   cudaStream_t s) {
+  if (bf16 && K % 8 == 0 && Kp % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 31) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const long long total8 = R * (Kp >> 3);
+    const unsigned grid = (unsigned)std::min<long long>((total8 + 255) / 256, 8 * kNumSMs);
+    split3_bf16x8_kernel<<<grid, 256, 0, s>>>(src, (__nv_bfloat16*)dst, R, K, Kp, ld, kind);
+    EP_LAUNCH_CHECK();
+    return 0;
+  }
   const long long total = R * Kp;
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 8 * kNumSMs);
   if (bf16) split3_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, (__nv_bfloat16*)dst, R, K, Kp, ld, kind);

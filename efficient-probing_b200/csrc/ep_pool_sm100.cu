@@ -651,13 +651,24 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t n, float scale,
-                                       float* __restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] = scale * sum_k part[k][i]: 32 outputs per block, the partials dealt over 8 thread rows and combined in
+// a fixed order (deterministic); 1024 blocks keep enough loads in flight for a ~19 MB read
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t n,
+                                                              float scale, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const size_t i = (size_t)blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int k = 0; k < nparts; ++k) s += part[(size_t)k * n + i];
-  out[i] = s * scale;
+  if (i < n)
+    for (int k = ty; k < nparts; k += 8) s += __ldg(part + (size_t)k * n + i);
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][tx];
+    out[i] = t * scale;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -893,7 +904,7 @@ int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int
   if ((rc = launch_kp<1>(x, B, N, D, M, pl, blocks, nullptr, part, &groups, 0, s))) return rc;
   tm.mark("kp<1> dq");
   const size_t n = (size_t)M * D;
-  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, groups, n, scale, d_cls);
+  reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(part, groups, n, scale, d_cls);
   EP_LAUNCH_CHECK();
   tm.mark("reduce");
   return 0;
