@@ -113,7 +113,7 @@ bool use_sm100(int x_dtype, int B, int N, int D, int M, int* rc);
 bool p_hilo(int x_dtype, int B, int N, int D, int M, int d_out) {
   int rc = 0;
   const int c = D / d_out / M;
-  return use_tc() && kSplitBf16 && c % 8 == 0 && D % 64 == 0 && B % 64 == 0 && use_sm100(x_dtype, B, N, D, M, &rc);
+  return use_tc() && kSplitBf16 && c % 4 == 0 && D % 64 == 0 && B % 64 == 0 && use_sm100(x_dtype, B, N, D, M, &rc);
 }
 bool use_sm100(int x_dtype, int B, int N, int D, int M, int* rc) {
   *rc = 0;
@@ -232,7 +232,7 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
   // delta[b, m] = sum_n A dA = dP[b, m] . P[b, m] = g[b, m, :] . (out[b, m, :] - bias[m, :])
   if ((rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
   const bool hilo = p_layout < 0 ? p_hilo(x_dtype, B, N, D, M, d_out) : p_layout == 1;
-  if (hilo && !(use_tc() && c % 8 == 0 && B % 64 == 0 && D % 64 == 0)) return EP_ERR_UNSUPPORTED;   // mode changed since ep_fwd
+  if (hilo && !(use_tc() && c % 4 == 0 && B % 64 == 0 && D % 64 == 0)) return EP_ERR_UNSUPPORTED;   // mode changed since ep_fwd
   if (use_tc() && c % 4 == 0) {
     // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch
     if (hilo) {

@@ -123,6 +123,8 @@ CASES = [  # B, N, D, M, K, d_out, bias, spread, q_gain
     (3, 1370, 768, 8, 10, 1, False, 1.0, 5.0),         # Franca@518 token count
     (150, 129, 256, 16, 10, 1, False, 1.0, 10.0),      # more samples than SMs, one token past a tile edge
     (7, 128, 128, 64, 10, 1, False, 1.0, 10.0),        # M = 64 (widest operand), N exactly one tile
+    (64, 40, 1152, 32, 10, 1, False, 1.0, 10.0),       # B % 64 == 0 with c = 36 (c % 8 != 0): hi/lo P, ragged column tiles
+    (128, 20, 256, 8, 16, 2, True, 1.0, 10.0),         # hi/lo P with d_out = 2 and bias
 ]
 
 
@@ -194,6 +196,39 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         head[0](torch.zeros(2, 5, 64, device=DEV), cls=torch.zeros(2, 4, 64, device=DEV))   # not (B, M, C): ep.py:35
     assert E._lib.load().ep_device_check() == 0
+
+
+@pytest.mark.parametrize("B", [64, 20], ids=["hilo_rows", "fp32"])
+def test_saved_pooled_tokens_vs_oracle(B):
+    """The saved tensor P of ep_fwd, in whichever layout ep_pooled_layout announces (bf16 hi/lo rows when the
+    tcgen05 GEMMs consume it, else fp32), against the oracle's pooled tokens; and the saved logits / statistics."""
+    lib = E._lib.load()
+    N, D, M = 70, 256, 8
+    p = O.build_head(D, M, 10, seed=0)
+    p.cls_token = p.cls_token * 10.0
+    x = O.synthetic_tokens(B, N, D, seed=21)
+    _, attn, P_ref, rmax_ref, rsum_ref = O.ep_forward_pooled(x.double(), p.cls_token.double(), p.v_weight.double(), None,
+                                                            p.scale, M, 1)
+    xg = x.to(DEV)
+    out, S, rmax, rsum = (torch.empty(s_, device=DEV) for s_ in ((B, D), (B, M, N), (B, M), (B, M)))
+    P = torch.empty(B, M, D, device=DEV)
+    ws = torch.empty(lib.ep_workspace_bytes(B, N, D, M, 1), dtype=torch.uint8, device=DEV)
+    cls, w = p.cls_token.to(DEV).contiguous(), p.v_weight.to(DEV).contiguous()
+    E._lib.check(lib.ep_fwd(xg.data_ptr(), 0, cls.data_ptr(), w.data_ptr(), None, float(p.scale), B, N, D, M, 1,
+                            out.data_ptr(), S.data_ptr(), rmax.data_ptr(), rsum.data_ptr(), P.data_ptr(), None,
+                            ws.data_ptr(), ws.numel(), E._lib.stream_ptr(torch.device(DEV))), "ep_fwd")
+    layout = lib.ep_pooled_layout(0, B, N, D, M, 1)
+    assert layout == (1 if B % 64 == 0 else 0)
+    if layout == 1:
+        hl = P.view(torch.bfloat16).reshape(B, M, 2, D).double()
+        assert float(hl[:, :, 1].abs().max()) <= float(hl[:, :, 0].abs().max()) * 2.0 ** -7     # lo is a correction
+        P_got = hl[:, :, 0] + hl[:, :, 1]
+    else:
+        P_got = P.double()
+    close(P_got, P_ref, 2e-5, "P")
+    close(rmax, rmax_ref, 1e-5, "rowmax")
+    close(rsum, rsum_ref, 1e-5, "rowsum")
+    close(torch.softmax(S.double(), -1), attn, 1e-5, "softmax(S)")
 
 
 def test_fused_and_separate_softmax_agree():

@@ -24,7 +24,7 @@ def pooled(P, xt, B, N, D, M, d_out):
         return hl[:, :, 0] + hl[:, :, 1]
     return P.double()
 for (B, N, D, M, d_out, xt) in [(256, 5, 256, 8, 1, 1), (130, 3, 128, 32, 1, 1), (64, 4, 256, 8, 2, 1), (256, 70, 256, 8, 1, 0),
-                                (128, 257, 1024, 32, 1, 0), (64, 197, 768, 12, 1, 0), (192, 100, 512, 8, 2, 0)]:
+                                (128, 257, 1024, 32, 1, 0), (64, 197, 768, 12, 1, 0), (192, 100, 512, 8, 2, 0), (64, 40, 1152, 32, 1, 0)]:
     Dp = D // d_out; c = Dp // M
     x = torch.randn(B, N, D, device=dev).to(torch.bfloat16 if xt == 0 else torch.float32)
     cls = torch.randn(M, D, device=dev) * 0.5; W = torch.randn(Dp, D, device=dev) * 0.1
