@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--pool", type=int, default=8, help="distinct resident batches cycled through")
     ap.add_argument("--cpu-sample", type=int, default=64, help="samples per CPU-baseline step")
+    ap.add_argument("--comm-sms", type=int, default=-1,
+                    help="SMs reserved for the overlapped all-reduce (N > 1); -1 = the trainer's default for N")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto, 1 general kernels, 2 tcgen05 only")
@@ -198,6 +200,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduce overlaps the token-streaming backward kernels, which leave `comm_sms` SMs free
+        # for it (EPHeadTrainer): keep the collective within them
+        if args.comm_sms < 0:
+            args.comm_sms = E.trainer.default_comm_sms(world)
+        if args.comm_sms > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))
         dist.init_process_group("nccl", device_id=dev)
     B, N, D, K, M = cfg["B"], cfg["N"], cfg["D"], cfg["K"], args.queries
     lib = E._lib.load()
@@ -205,7 +213,7 @@ def main():
 
     torch.manual_seed(0)                                         # identical init on every rank (DDP broadcast)
     head = E.make_ep_head(D, M, K).to(dev)
-    tr = E.EPHeadTrainer(head, B, N, lr=0.1, use_graph=not args.no_graph)
+    tr = E.EPHeadTrainer(head, B, N, lr=0.1, use_graph=not args.no_graph, comm_sms=args.comm_sms)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)   # data seed = seed + rank (main_linprobe.py:517)
     pool_x, pool_y = [], []
     for i in range(args.pool):
@@ -322,7 +330,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"EP head (M={M}) on {cfg['name']}, per-GPU batch {B}, {K} classes, "
                                    f"fwd+bwd+allreduce+LARS", "per_gpu_batch": B, "global_batch": B * world,
-                       "tokens": N, "dim": D, "queries": M, "classes": K, "parallelism": f"dp{world}",
+                       "tokens": N, "dim": D, "queries": M, "classes": K, "parallelism": f"dp{world}", "comm_sms": tr.comm_sms,
                        "l2": f"inputs larger than L2: {args.pool} resident batches x {alg_bytes / 1e6:.0f} MB cycled",
                        "cuda_graph": not args.no_graph, "kernel_family": fam},
             "clocks": clocks,

@@ -58,6 +58,11 @@ extern "C" int ep_timing_get(int i, char* name, int name_len, float* us) {
   return 0;
 }
 extern "C" int ep_timing_reset(void) { ep::g_ntimings = 0; return 0; }
+extern "C" int ep_set_sm_limit(int n) {
+  if (n < 0) return EP_ERR_SHAPE;
+  ep::g_sm_limit = n;
+  return 0;
+}
 extern "C" int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M) {
   if (g_kernel_mode == 1) return 1;
   return sm100_supported(x_dtype, B, N, D, M) ? 2 : (g_kernel_mode == 2 ? 0 : 1);

@@ -24,6 +24,8 @@ namespace ep {
 
 extern unsigned long long g_launch_count;     // kernels launched by this library in this process
 constexpr int kNumSMs = 148;
+extern int g_sm_limit;                 // ep_set_sm_limit: CTAs the persistent token-streaming kernels may launch (0 = all SMs)
+inline int stream_sms() { return g_sm_limit > 0 && g_sm_limit < kNumSMs ? g_sm_limit : kNumSMs; }
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -30,6 +30,7 @@
 
 namespace ep {
 using namespace ptx;
+int g_sm_limit = 0;
 int g_debug = 0;        // developer knob (ep_set_debug): bit 0 = converter skips global loads, bit 1 = no P stores
 
 constexpr int kTileRows = 128;    // ks: token rows per MMA tile (UMMA M)
@@ -789,7 +790,7 @@ int launch_ks(const void* x, const void* w, int w_batched, int B, int N, int D, 
   const size_t smem = pl.ks_smem + (kMode == 2 ? kStatBytes : 0);
   if (smem > 227 * 1024) return EP_ERR_UNSUPPORTED;
   if ((rc = set_dyn_smem(ks_kernel<kMode>, smem))) return rc;
-  const int grid = std::min(B * pl.ngroups, kNumSMs);
+  const int grid = std::min(B * pl.ngroups, stream_sms());
   ks_kernel<kMode><<<grid, kThreads, smem, s>>>(tm_x, tm_xt, tm_w, p);
   EP_LAUNCH_CHECK();
   return 0;
@@ -814,7 +815,7 @@ int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const u
   p.debug = g_debug;
   p.round_out = round_out;
   if ((rc = set_dyn_smem(kp_kernel<kMode>, pl.kp_smem))) return rc;
-  const int gx = std::max(1, std::min(B, kNumSMs / ysplit));
+  const int gx = std::max(1, std::min(B, stream_sms() / ysplit));
   if (groups_out) *groups_out = gx;
   kp_kernel<kMode><<<dim3(gx, ysplit), kThreads, pl.kp_smem, s>>>(tm_x, p);
   EP_LAUNCH_CHECK();

@@ -30,13 +30,22 @@ from .optim import lars_launch, adamw_launch, sgd_launch
 BN_EPS_DEFAULT = 1e-6
 
 
+def default_comm_sms(world: int) -> int:
+    """SMs the streaming backward kernels leave to the overlapped all-reduce (see EPHeadTrainer, comm_sms)."""
+    return 16 if world >= 4 else 0
+
+
 class EPHeadTrainer:
     def __init__(self, head: nn.Sequential, batch_size: int, num_tokens: int, *, lr: float = 0.1,
                  weight_decay: float = 0.0, momentum: float = 0.9, trust_coefficient: float = 0.001,
                  x_dtype: torch.dtype = torch.bfloat16, process_group=None, use_graph: bool = True,
                  overlap_comm: bool = True, optimizer: str = "lars", betas=(0.9, 0.999), eps: float = 1e-8,
-                 accum_iter: int = 1):
-        """optimizer: "lars" (util/lars.py, the published protocol), "adamw" (torch.optim.AdamW defaults) or "sgd"
+                 accum_iter: int = 1, comm_sms: Optional[int] = None):
+        """comm_sms: SMs left free for the overlapped gradient all-reduce while the token-streaming half of the
+        backward pass runs (multi-GPU only; pair it with NCCL_MAX_CTAS <= comm_sms set before the process group is
+        created -- bench.py does -- so the collective's CTAs fit there).  None = default_comm_sms(world): measured
+        on B200/NVSwitch, c2: 8 GPUs 0.827 ms/step with 0, 0.789 with 8, 0.767 with 16; 2 GPUs are fastest with 0.
+        optimizer: "lars" (util/lars.py, the published protocol), "adamw" (torch.optim.AdamW defaults) or "sgd"
         (torch.optim.SGD, momentum as given) -- the three main_linprobe.py:403-408 can build.
         accum_iter: gradient accumulation as engine_finetune.py:72-77 (loss / accum_iter, optimizer every k-th call)."""
         if optimizer not in ("lars", "adamw", "sgd"):
@@ -66,6 +75,7 @@ class EPHeadTrainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = use_graph
         self.overlap_comm = overlap_comm and self.world > 1
+        self.comm_sms = (default_comm_sms(self.world) if comm_sms is None else int(comm_sms)) if self.overlap_comm else 0
 
         f32 = dict(dtype=torch.float32, device=dev)
         B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
@@ -179,6 +189,15 @@ class EPHeadTrainer:
         """token-streaming half of the backward pass: d cls_token"""
         lib, s = self.lib, _lib.stream_ptr(self.dev)
         pool = self.pool
+        if self.comm_sms > 0:          # the early all-reduce runs underneath: leave it SMs (statically scheduled CTAs
+            lib.ep_set_sm_limit(max(1, torch.cuda.get_device_properties(self.dev).multi_processor_count - self.comm_sms))
+        try:
+            self._bwd_pool(lib, s, pool)
+        finally:
+            if self.comm_sms > 0:      # that land behind a collective's CTA would stretch the kernel by its duration)
+                lib.ep_set_sm_limit(0)
+
+    def _bwd_pool(self, lib, s, pool):
         _lib.check(lib.ep_bwd_pool(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
                                    float(pool.scale), self.B, self.N, self.D, self.M, self.d_out, self.S.data_ptr(),
                                    self.rowmax.data_ptr(), self.rowsum.data_ptr(), self.g["cls"].data_ptr(),

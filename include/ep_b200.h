@@ -52,6 +52,11 @@ int ep_set_kernel_mode(int mode);
  * 0 (default) = TF32 tensor cores, operands rounded to nearest tf32, fp32 accumulate (~3e-4 relative);
  * 1 = fp32 FMA on the CUDA cores (evaluation, where top-1 decisions must not move). */
 int ep_set_gemm_mode(int mode);
+/* Number of CTAs the persistent token-streaming kernels (one CTA per SM) launch from now on; 0 = one per SM of
+ * the device (default).  A data-parallel caller lowers it around ep_bwd_pool so that the gradient all-reduce it
+ * overlaps with that call (main_linprobe.py:581-583) finds free SMs instead of delaying statically scheduled
+ * CTAs.  Process-wide; read at launch (i.e. at capture time for CUDA graphs). */
+int ep_set_sm_limit(int n);
 /* Which family the last ep_fwd/ep_bwd call on this thread used (1 = general, 2 = tcgen05). */
 int ep_last_kernel_family(void);
 /* Developer knob: bit 5 (32) makes ep_fwd / ep_bwd_proj / ep_bwd_pool bracket each of their kernels with
