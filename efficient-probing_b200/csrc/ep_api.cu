@@ -9,7 +9,7 @@ using namespace ep;
 
 unsigned long long ep::g_launch_count = 0;
 namespace ep { extern int g_debug; }
-static int g_gemm_mode = 0;                   // 0 = TF32 tensor cores, 1 = fp32 CUDA cores
+static int g_gemm_mode = 0;                   // 0 = tensor cores (3-term bf16 / TF32 products), 1 = fp32 CUDA cores
 static int g_kernel_mode = 0;                 // 0 auto, 1 general, 2 tcgen05
 static thread_local int t_last_family = 0;
 
@@ -71,7 +71,7 @@ extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count;
 
 namespace {
 struct Ws {                      // workspace layout
-  size_t dP, delta, slots, sm100, w_r, w_t, g_r, g_t, total;
+  size_t dP, delta, slots, sm100, w_t, g_r, g_t, total;
 };
 // The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
@@ -91,7 +91,6 @@ int dp_nt(int D) { return std::min(256, (D + 31) / 32 * 32); }     // column til
 Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
-  w.w_r = off;   off += 0;                                                   // (unused)
   w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
   w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
   w.g_t = off;   off += align_up((size_t)3 * B * D * 2, 256);               // bf16 [hi|hi|lo] copy of g_out^T

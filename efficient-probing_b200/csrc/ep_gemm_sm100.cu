@@ -1,9 +1,12 @@
-// TF32 tensor-core GEMM (tcgen05.mma kind::tf32, fp32 operands straight from global memory through TMA,
-// fp32 accumulate in TMEM) for the small dense contractions of the EP head:
-//   value projection of the pooled tokens and its two gradients (batched over the M queries),
-//   the classifier (probe_heads.py:76) and its two gradients.
-// One CTA computes one 128 x NT output tile of one batch entry: warp 0 = TMA producer, warp 1 = MMA
-// issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Persistent tcgen05 GEMM (operands through TMA, fp32 accumulate in TMEM) for the small dense contractions of
+// the EP head: value projection of the pooled tokens and its two gradients (batched over the M queries), the
+// classifier (probe_heads.py:76) and its input gradient.
+// Operand types: bf16 (kind::f16; the callers pass fp32 data as bf16 hi/lo pairs) or fp32 read as tf32
+// (kind::tf32, K-major only).  fp32-accurate products come from three bf16 terms, either concatenated along K by
+// the caller or -- GemmTC::x3 -- issued here from hi and lo tiles that share a pipeline stage.
+// Each CTA walks 128 x NT output tiles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-11 = epilogue (TMEM -> registers -> 256-bit global stores); the accumulator is
+// double-buffered in TMEM so a tile's epilogue overlaps the next tile's loads and MMAs.
 // Either operand may be K-major (contraction index contiguous in memory) or MN-major (output index
 // contiguous); the same 128-byte-swizzled shared-memory bytes serve both through the descriptor's
 // major bit, so no operand is ever transposed or converted on the way.

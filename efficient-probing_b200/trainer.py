@@ -50,8 +50,6 @@ class EPHeadTrainer:
         accum_iter: gradient accumulation as engine_finetune.py:72-77 (loss / accum_iter, optimizer every k-th call)."""
         if optimizer not in ("lars", "adamw", "sgd"):
             raise ValueError("optimizer must be 'lars', 'adamw' or 'sgd'")
-        if optimizer == "sgd" and momentum == 0.9 and False:
-            pass
         self.optimizer, self.betas, self.eps_opt, self.accum_iter = optimizer, betas, eps, max(1, int(accum_iter))
         pool, bn, fc = head[0], head[1], head[2]
         if not isinstance(pool, EfficientProbing) or not isinstance(bn, nn.BatchNorm1d) or not isinstance(fc, nn.Linear):

@@ -49,8 +49,10 @@ int ep_device_check(void);
  * general kernels), 1 = force the general CUDA-core kernels, 2 = force tcgen05 (error if unsupported). */
 int ep_set_kernel_mode(int mode);
 /* Precision of the head's small dense contractions (value projection, classifier and their gradients):
- * 0 (default) = TF32 tensor cores, operands rounded to nearest tf32, fp32 accumulate (~3e-4 relative);
- * 1 = fp32 FMA on the CUDA cores (evaluation, where top-1 decisions must not move). */
+ * 0 (default) = tensor cores, fp32 accumulate: three-term bf16 / TF32 products (~5e-6 relative) in the tcgen05
+ *     GEMMs, plain TF32 (~3e-4) in the mma.sync weight-gradient kernel;
+ * 1 = fp32 FMA on the CUDA cores (evaluation, where top-1 decisions must not move).
+ * Like the kernel mode it must not change between a forward and its backward (it decides the layout of P). */
 int ep_set_gemm_mode(int mode);
 /* Number of CTAs the persistent token-streaming kernels (one CTA per SM) launch from now on; 0 = one per SM of
  * the device (default).  A data-parallel caller lowers it around ep_bwd_pool so that the gradient all-reduce it

@@ -38,6 +38,14 @@ def test_argument_rejection_needs_no_gpu():
     assert L.ep_workspace_bytes(0, 1, 1, 1, 1) == 0
     assert L.ep_workspace_bytes(4, 19, 64, 8, 1) > 0
     assert L.ep_set_kernel_mode(7) == -2 and L.ep_set_kernel_mode(0) == 0
+    # the extended entry points check their arguments the same way
+    assert L.ep_fwd_ex(None, 0, None, 1, None, None, 1.0, 1, 1, 8, 1, 1, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.ep_bwd_ex(None, 0, None, 0, None, 1.0, 1, 1, 8, 1, 1, None, None, None, None, 0, None, None, None, None, None,
+                       None, None, None, 0, None) == -1
+    assert L.ep_pooled_layout(0, 4, 19, 64, 5, 1) == -2          # 64 % 5 != 0
+    assert L.ep_pooled_layout(1, 64, 19, 128, 8, 1) == 0         # fp32 tokens: general kernels, fp32 P
+    assert L.ep_set_sm_limit(-1) == -2 and L.ep_set_sm_limit(0) == 0
+    assert L.ep_linear_workspace_bytes(8, 72, 10) >= 3 * 2 * (10 * 128 + 72 * 64 + 8 * 128 + 8 * 64)   # padded thirds
 
 
 def test_module_surface_matches_reference_fingerprints():
