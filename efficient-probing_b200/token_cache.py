@@ -62,7 +62,7 @@ class TokenShard:
             raise ValueError(f"{path}: not an {MAGIC} token shard")
         self.path, self.header = path, header
         self.n, self.N, self.C = header["n"], header["N"], header["C"]
-        mm = np.memmap(path, dtype=np.uint8, mode="r")
+        mm = np.memmap(path, dtype=np.uint8, mode="c")            # copy-on-write: torch wants a writable array, the file is never written
         tok = mm[header["tokens_offset"]: header["tokens_offset"] + self.n * self.N * self.C * 2]
         lab = mm[header["labels_offset"]: header["labels_offset"] + self.n * 8]
         self.tokens = torch.from_numpy(tok.view(np.int16).reshape(self.n, self.N, self.C)).view(torch.bfloat16)
@@ -118,13 +118,22 @@ class TokenStream:
         return (self.total - self.total % self.world) // self.world // self.batch
 
     def _gather(self, idx: torch.Tensor, slot: int):
+        """Rows `idx` (global sample numbers) of the shards -> the slot's pinned buffers, one vectorised gather per
+        shard touched (a per-sample Python loop costs ~20 us a row: 20 ms per 1024-sample batch, twice the H2D copy)."""
+        hx, hy = self._hx[slot], self._hy[slot]
         idx_np = idx.numpy()
         shard_id = np.searchsorted(self.offsets, idx_np, side="right") - 1
-        for j, (s, i) in enumerate(zip(shard_id, idx_np)):
+        for s in np.unique(shard_id):
             sh = self.shards[int(s)]
-            k = int(i - self.offsets[s])
-            self._hx[slot][j].copy_(sh.tokens[k])
-            self._hy[slot][j] = sh.labels[k]
+            pos = np.nonzero(shard_id == s)[0]
+            local = torch.from_numpy(idx_np[pos] - self.offsets[s])
+            if len(pos) == len(idx_np):                    # the whole batch comes from this shard: gather in place
+                torch.index_select(sh.tokens, 0, local, out=hx)
+                torch.index_select(sh.labels, 0, local, out=hy)
+            else:
+                pos_t = torch.from_numpy(pos)
+                hx.index_copy_(0, pos_t, sh.tokens.index_select(0, local))
+                hy.index_copy_(0, pos_t, sh.labels.index_select(0, local))
 
     def _stage(self, idx: torch.Tensor, slot: int):
         self._free[slot].synchronize()                       # the consumer has finished with this slot
