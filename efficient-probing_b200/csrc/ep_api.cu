@@ -78,7 +78,7 @@ struct Ws {                      // workspace layout
 // 3-term operand copies of the K-concatenated GEMMs: bf16 hi/lo (kind::f16, half the bytes, twice the MMA
 // rate) rather than tf32 big/small; both give ~1e-5.  bf16 rows need K % 8 == 0 for 16-byte TMA strides.
 constexpr int kSplitBf16 = 1;
-bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !(ep::g_debug & 128); }
+bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0; }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 // column tile of the classifier GEMMs: the narrowest that still gives every SM a tile
 int lin_nt(int rows, int cols) {

@@ -106,12 +106,10 @@ int launch_gemm_v0(const GemmDesc& g, cudaStream_t s);
 int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s);            // out[j] = sum_i a[i][j]
 int launch_delta_from_out(const float* g, const float* out, const float* bias, long long rows, int M, int c,
                           float* delta, cudaStream_t s);
-int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s);  // out[i] = a[i].b[i]
 
 // TF32 tensor-core GEMM (ep_gemm_sm100.cu)
 struct GemmTC;
 bool gemm_tc_available();
-int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s);
 // C[z][i][j] = sum_k A.. B..; see ep_api.cu for the operand descriptions
 enum TcOperand { TC_KMAJOR = 0, TC_MNMAJOR = 1 };
 struct TcSide {            // one operand as a 3-D fp32 tensor (d0 contiguous) and how tiles index it

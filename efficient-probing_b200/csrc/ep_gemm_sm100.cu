@@ -45,7 +45,6 @@ struct GemmTC {
   int epi_mode;
   __nv_bfloat16* hl;                          // (B, Jrows, D)
   int Jrows;
-  int debug;
 };
 
 __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
@@ -275,16 +274,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// elementwise round-to-nearest to tf32 (operands of the TF32 GEMMs are pre-rounded so that the tensor
-// core's truncation of the low mantissa bits is exact; an un-rounded operand would bias every product)
-__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(src)[i];
-    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-    reinterpret_cast<float4*>(dst)[i] = v;
-  }
-}
-
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -351,7 +340,7 @@ int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int
   g.I = I; g.J = J; g.K = K; g.NT = NT;
   g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
-  g.epi_mode = 1; g.hl = (__nv_bfloat16*)hl; g.Jrows = Jrows; g.debug = g_debug;
+  g.epi_mode = 1; g.hl = (__nv_bfloat16*)hl; g.Jrows = Jrows;
   g.bf16 = A.bf16; g.a_zmul = 1;
   return launch_gemm_tc(ta, tb, g, Z, s);
 }
@@ -367,7 +356,7 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
   g.a_mn = A.mn_major; g.b_mn = B.mn_major; g.a_swap = A.swap; g.b_swap = B.swap;
   g.a_zdiv = A.zdiv > 0 ? A.zdiv : 1; g.b_zdiv = B.zdiv > 0 ? B.zdiv : 1;
   g.C = C; g.bias = bias; g.c_row = c_row; g.c_col = c_col; g.c_z = c_z; g.bias_z = bias_z;
-  g.round_tf32 = round_out; g.debug = g_debug;
+  g.round_tf32 = round_out;
   g.bf16 = A.bf16;
   g.a_zmul = 1;
   if (A.lo_k || A.lo_z || B.lo_k) {                            // hi/lo operand pairs: 3-term product
@@ -375,13 +364,6 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
     g.x3 = 1; g.a_zmul = A.zmul > 0 ? A.zmul : 1; g.a_lo_z = A.lo_z; g.a_lo_k = A.lo_k; g.b_lo_k = B.lo_k;
   }
   return launch_gemm_tc(ta, tb, g, Z, s);
-}
-
-int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s) {
-  const size_t n4 = n / 4;
-  round_tf32_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, 4 * kNumSMs), 256, 0, s>>>(src, dst, n4);
-  EP_LAUNCH_CHECK();
-  return 0;
 }
 
 }  // namespace ep

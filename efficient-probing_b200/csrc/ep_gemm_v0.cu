@@ -94,21 +94,6 @@ int launch_colsum(const float* a, int rows, int cols, float* out, cudaStream_t s
 }
 
 // out[i] = a[i] . b[i], one warp per row   (delta = dP . P)
-__global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long rows, int cols,
-                              float* __restrict__ out) {
-  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const float4* pa = reinterpret_cast<const float4*>(a + r * cols);
-  const float4* pb = reinterpret_cast<const float4*>(b + r * cols);
-  float s = 0.f;
-  for (int c = lane; c < cols / 4; c += 32) {
-    const float4 u = __ldg(pa + c), v = __ldg(pb + c);
-    s += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
-  }
-  s = warp_sum(s);
-  if (lane == 0) out[r] = s;
-}
 // delta[b, m] = sum_j g[b, m*c + j] * (out[b, m*c + j] - bias[m*c + j]).  Since out - bias = W_m . P[b, m], this
 // equals dP[b, m] . P[b, m] = sum_n A dA (the softmax-backward row term) without touching the (B, M, D) tensors.
 __global__ void delta_from_out_kernel(const float* __restrict__ g, const float* __restrict__ out,
@@ -132,11 +117,6 @@ int launch_delta_from_out(const float* g, const float* out, const float* bias, l
   return 0;
 }
 
-int launch_rowdot(const float* a, const float* b, long long rows, int cols, float* out, cudaStream_t s) {
-  rowdot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a, b, rows, cols, out);
-  EP_LAUNCH_CHECK();
-  return 0;
-}
 
 }  // namespace ep
 

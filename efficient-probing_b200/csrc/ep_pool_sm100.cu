@@ -31,7 +31,7 @@
 namespace ep {
 using namespace ptx;
 int g_sm_limit = 0;
-int g_debug = 0;        // developer knob (ep_set_debug): bit 0 = converter skips global loads, bit 1 = no P stores
+int g_debug = 0;        // developer knobs (ep_set_debug, see include/ep_b200.h)
 
 constexpr int kTileRows = 128;    // ks: token rows per MMA tile (UMMA M)
 constexpr int kChunkD = 64;       // bf16 elements per 128-byte swizzle row
@@ -54,7 +54,7 @@ struct KSParams {
 };
 
 struct KPParams {
-  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, debug, round_out;
+  int B, N, D, M, J, nkb, nsl, xslots, wslots, nbuf, bufcols, tmem_cols, round_out;
   const uint8_t* blocks; // operand blocks [B][nkb][J x 64 tokens]: exp(S - rowmax) (mode 0) or dS (mode 1)
   const float* rsum;     // mode 0
   float* out;            // mode 0: P (B, M, D) fp32, or bf16 hi/lo rows (B, M, 2, D) when round_out; mode 1: partial dq
@@ -479,9 +479,8 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t accum = (kMode == 0) ? (uint32_t)((kb | k) != 0) : (uint32_t)(!(first && kb == 0 && k == 0));
-              if (!(p.debug & 16))
-                umma_f16(acc + (uint32_t)(sl * p.J), smem_desc_sw128(xsm + 2048u * k, kBrickBytes / 2, 1024),
-                         smem_desc_sw128(wsm + 32u * k, 16, 1024), idesc, accum);
+              umma_f16(acc + (uint32_t)(sl * p.J), smem_desc_sw128(xsm + 2048u * k, kBrickBytes / 2, 1024),
+                       smem_desc_sw128(wsm + 32u * k, 16, 1024), idesc, accum);
             }
             umma_commit(xempty(xs));
             if (++xs == p.xslots) { xs = 0; xph ^= 1u; }
@@ -506,7 +505,7 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
         for (int h = 0; h < 2; ++h)
           if (h * 32 + lane < p.M) invl[h] = 1.f / __ldg(p.rsum + (size_t)b * p.M + h * 32 + lane);
       }
-      for (int u = eh; u < ((p.debug & 8) ? 0 : nsl * upt); u += 2) {
+      for (int u = eh; u < nsl * upt; u += 2) {
         const int sl = u / upt, j0 = (u - sl * upt) << 4;
         const int d = d0 + sl * 128 + wq * 32 + lane;
         uint32_t r[16];
@@ -525,7 +524,7 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
                 __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
                 pr[0] = hi;
                 pr[p.D] = lo;
-              } else if (!(p.debug & 2)) {
+              } else {
                 p.out[((size_t)b * p.M + m) * p.D + d] = v;
               }
             } else {
@@ -804,15 +803,13 @@ int launch_kp(const void* x, int B, int N, int D, int M, const Plan& pl, const u
   if ((rc = make_tmap(&tm_x, x, D, N, B, kTokBlock))) return rc;
   KPParams p{};
   p.B = B; p.N = N; p.D = D; p.M = M; p.J = pl.J; p.nkb = pl.nkb;
-  const bool wide = (g_debug & 64) != 0;                      // experiment: forward with the backward's D split
-  p.nsl = (kMode == 0 && !wide) ? pl.nsl_fwd : pl.nsl_bwd;
-  const int ysplit = (kMode == 0 && !wide) ? pl.ysplit_fwd : pl.ysplit_bwd;
+  p.nsl = kMode == 0 ? pl.nsl_fwd : pl.nsl_bwd;
+  const int ysplit = kMode == 0 ? pl.ysplit_fwd : pl.ysplit_bwd;
   p.xslots = pl.xslots; p.wslots = pl.wslots;
   p.bufcols = p.nsl * pl.J;
   p.nbuf = (kMode == 0 && 2 * p.bufcols <= 512) ? 2 : 1;
   p.tmem_cols = pow2_cols(p.nbuf * p.bufcols);
   p.blocks = blocks; p.rsum = rsum; p.out = out;
-  p.debug = g_debug;
   p.round_out = round_out;
   if ((rc = set_dyn_smem(kp_kernel<kMode>, pl.kp_smem))) return rc;
   const int gx = std::max(1, std::min(B, stream_sms() / ysplit));

@@ -64,8 +64,7 @@ int ep_last_kernel_family(void);
 /* Developer knob: bit 5 (32) makes ep_fwd / ep_bwd_proj / ep_bwd_pool bracket each of their kernels with
  * CUDA events on the call's stream (one host sync per call) and record the durations, read back with
  * ep_timing_*; bit 8 (256) also prints them; bit 9 (512) runs the forward softmax as a separate kernel instead
- * of in the logit kernel's epilogue (same results).  Other bits are performance experiments that make the
- * results WRONG.  0 in normal use. */
+ * of in the logit kernel's epilogue (same results).  Other bits are ignored.  0 in normal use. */
 int ep_set_debug(int flags);
 int ep_timing_count(void);
 int ep_timing_get(int i, char* name, int name_len, float* microseconds);
