@@ -67,3 +67,32 @@ def test_head_files_both_formats(tmp_path):
     assert torch.equal(h[0].cls_token, head[0].cls_token)
     with pytest.raises(ValueError):
         E.load_head({"model": {"head.weight": torch.zeros(3, 3)}})
+
+
+def test_batch_gather_across_shards_matches_row_lookup(tmp_path):
+    """TokenStream._gather (the host side of the loader) on CPU buffers: rows from several shards, repeated rows,
+    a batch from a single shard -- against a per-row lookup."""
+    import numpy as np
+    from efficient_probing_b200 import token_cache as T
+    g = torch.Generator().manual_seed(0)
+    shards = []
+    for i, n in enumerate([37, 50, 13]):
+        path = str(tmp_path / f"s{i}.eptok")
+        T.write_shard(path, torch.randn(n, 5, 16, generator=g), torch.randint(0, 10, (n,), generator=g))
+        shards.append(T.TokenShard(path))
+
+    class HostOnly(T.TokenStream):                     # the gather needs only the shard table and one buffer pair
+        def __init__(self, shards, batch):
+            self.shards, self.batch = list(shards), batch
+            self.offsets = np.cumsum([0] + [len(s) for s in shards])
+            self._hx = [torch.empty(batch, 5, 16, dtype=torch.bfloat16)]
+            self._hy = [torch.empty(batch, dtype=torch.int64)]
+
+    for idx in (torch.tensor([0, 99, 36, 37, 40, 86, 87, 5]), torch.tensor([40, 41, 38, 86, 50, 37]),
+                torch.tensor([3, 3, 0, 36])):
+        st = HostOnly(shards, len(idx))
+        st._gather(idx, 0)
+        for j, i in enumerate(idx.tolist()):
+            sh = int(np.searchsorted(st.offsets, i, side="right") - 1)
+            k = i - int(st.offsets[sh])
+            assert torch.equal(st._hx[0][j], shards[sh].tokens[k]) and int(st._hy[0][j]) == int(shards[sh].labels[k])
