@@ -706,6 +706,22 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64
   return r == CUDA_SUCCESS ? 0 : EP_ERR_UNSUPPORTED;
 }
 
+}  // namespace
+int make_tmap_bf16(::CUtensorMap_st* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || rank < 1 || rank > 5) return EP_ERR_DEVICE;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(m), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d,
+                  st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : EP_ERR_UNSUPPORTED;
+}
+namespace {
+
 int round16(int v) { return (v + 15) / 16 * 16; }
 int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 
@@ -844,6 +860,12 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
   EP_LAUNCH_CHECK();
   tm.mark("split_q");
+  // one-pass kernel: logits, softmax and pooled tokens of a sample without leaving the SM (ep_fused_sm100.cu)
+  if (attn == nullptr && P != nullptr && !(g_debug & 1024) && fused_supported(N, D, M)) {
+    rc = fused_pool_fwd(x, qhl, pl.J, B, N, D, M, P, S, rowmax, rowsum, round_p, s);
+    tm.mark("fused fwd");
+    return rc;
+  }
   // the softmax rides in the logit kernel's epilogue when one accumulator buffer holds the whole sample
   const bool fused = pl.ngroups == 1 && attn == nullptr && P != nullptr && !(g_debug & 512) &&
                      pl.ks_smem + kStatBytes <= 227 * 1024;
@@ -896,11 +918,17 @@ int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int
     EP_LAUNCH_CHECK();
     tm.mark("split_dP");
   }
-  if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, nullptr, blocks, S, rowmax, rowsum, delta, ndelta, s))) return rc;
-  tm.mark("ks<1> dS");
   int groups = 0;
-  if ((rc = launch_kp<1>(x, B, N, D, M, pl, blocks, nullptr, part, &groups, 0, s))) return rc;
-  tm.mark("kp<1> dq");
+  if (ndelta == 1 && !(g_debug & 1024) && fused_supported(N, D, M)) {
+    // one-pass kernel: dA, dS and the query gradient of a sample without leaving the SM (ep_fused_sm100.cu)
+    if ((rc = fused_pool_bwd(x, dphl, pl.J, B, N, D, M, S, rowmax, rowsum, delta, part, &groups, s))) return rc;
+    tm.mark("fused bwd");
+  } else {
+    if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, nullptr, blocks, S, rowmax, rowsum, delta, ndelta, s))) return rc;
+    tm.mark("ks<1> dS");
+    if ((rc = launch_kp<1>(x, B, N, D, M, pl, blocks, nullptr, part, &groups, 0, s))) return rc;
+    tm.mark("kp<1> dq");
+  }
   const size_t n = (size_t)M * D;
   reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(part, groups, n, scale, d_cls);
   EP_LAUNCH_CHECK();

@@ -238,6 +238,30 @@ def head_loss_and_grads(p: EPParams, x, targets, dtype=torch.float32) -> Dict[st
     return res
 
 
+def head_loss_and_grads_pooled(p: EPParams, x, targets, dtype=torch.float64) -> Dict[str, torch.Tensor]:
+    """Same result as head_loss_and_grads, computed through the pool-then-project closed form
+    (ep_forward_pooled + autograd of BN/Linear/CE only + ep_backward_pooled): no (B, N, D') value tensor,
+    so BASELINE-sized batches finish in seconds.  tests/test_oracle.py holds it to head_loss_and_grads."""
+    q = p.clone(dtype)
+    xd = x.to(dtype)
+    out, attn, P, rowmax, rowsum = ep_forward_pooled(xd, q.cls_token, q.v_weight, q.v_bias, q.scale,
+                                                     q.num_queries, q.d_out)
+    out_leaf = out.detach().requires_grad_(True)
+    fcw, fcb = q.fc_weight.requires_grad_(True), q.fc_bias.requires_grad_(True)
+    y, rm, rv, _ = batchnorm_train(out_leaf, q.running_mean, q.running_var, q.num_batches_tracked)
+    logits = F.linear(y, fcw, fcb)
+    loss = cross_entropy(logits, targets)
+    g_out, g_fcw, g_fcb = torch.autograd.grad(loss, [out_leaf, fcw, fcb])
+    cf = ep_backward_pooled(xd, q.cls_token, q.v_weight, q.scale, q.num_queries, q.d_out, attn, P, g_out)
+    res = {"loss": loss.detach(), "logits": logits.detach(), "attn": attn, "out": out, "y": y.detach(),
+           "running_mean": rm.detach(), "running_var": rv.detach(), "P": P, "rowmax": rowmax, "rowsum": rowsum,
+           "g_out": g_out, "grad.0.cls_token": cf["d_cls_token"], "grad.0.v.weight": cf["d_v_weight"],
+           "grad.2.weight": g_fcw, "grad.2.bias": g_fcb}
+    if q.v_bias is not None:
+        res["grad.0.v.bias"] = cf["d_v_bias"]
+    return res
+
+
 # --------------------------------------------------------------------------------------------
 # optimizer + schedule
 # --------------------------------------------------------------------------------------------

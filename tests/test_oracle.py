@@ -127,3 +127,15 @@ def test_invalid_configs_raise_like_reference():
     with pytest.raises(RuntimeError):
         cls, w, b, s = O.ep_init(64, num_queries=5)       # 64 % 5 != 0 -> reshape fails (ep.py:40)
         O.ep_forward(torch.randn(2, 3, 64), cls, w, b, s, 5, 1)
+
+
+def test_pooled_head_grads_equal_reference_formulation(golden):
+    """head_loss_and_grads_pooled (closed form, used for BASELINE-sized GPU parity cases) == autograd through the
+    reference formulation, every gradient and the loss."""
+    p = golden.params(torch.float64)
+    a = O.head_loss_and_grads(p, golden.t("x"), golden.t("targets"), dtype=torch.float64)
+    b = O.head_loss_and_grads_pooled(p, golden.t("x"), golden.t("targets"), dtype=torch.float64)
+    assert abs(float(a["loss"]) - float(b["loss"])) < 1e-12
+    for k in a:
+        if k.startswith("grad.") or k in ("logits", "out", "attn", "running_mean", "running_var"):
+            assert (a[k] - b[k]).norm() <= 1e-10 * a[k].norm() + 1e-14, k
