@@ -29,6 +29,7 @@ _SIGNATURES = {
     "ep_timing_count": (c_int, []),
     "ep_timing_get": (c_int, [c_int, ctypes.c_char_p, c_int, ctypes.POINTER(c_float)]),
     "ep_timing_reset": (c_int, []),
+    "ep_debug_trace": (c_int, [c_void_p, c_int]),
     "ep_set_sm_limit": (c_int, [c_int]),
     "ep_kernel_family_for": (c_int, [c_int] * 5),
     "ep_pooled_layout": (c_int, [c_int] * 6),

@@ -58,6 +58,10 @@ extern "C" int ep_timing_get(int i, char* name, int name_len, float* us) {
   return 0;
 }
 extern "C" int ep_timing_reset(void) { ep::g_ntimings = 0; return 0; }
+extern "C" int ep_debug_trace(long long* host_out, int n) {
+  if (!host_out || n < 1) return EP_ERR_NULL;
+  return fused_trace_fetch(host_out, n);
+}
 extern "C" int ep_set_sm_limit(int n) {
   if (n < 0) return EP_ERR_SHAPE;
   ep::g_sm_limit = n;

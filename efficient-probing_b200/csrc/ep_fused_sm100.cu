@@ -3,25 +3,43 @@
 //   forward   (poolings/ep.py:39-45)   S = x q^T  ->  softmax over tokens  ->  P = A x           in one kernel
 //   backward      dA = x dP^T -> dS = A (dA - delta)  ->  dq += dS^T x      in one kernel
 //
-// A sample (N x D bf16: 526 KB at N=257, D=1024) fits neither shared memory nor, with the pooled accumulators,
-// a one-shot TMEM plan, and the softmax needs all of a sample's logits before the first pooled product.  So a
-// persistent CTA walks its samples and fetches each one twice, back to back, through ONE TMA ring:
+// A sample (N x D bf16: 526 KB at N=257, D=1024) does not fit shared memory, and the softmax needs all of a
+// sample's logits before the first pooled product.  So a persistent CTA walks its samples and fetches each one
+// twice through TMA:
 //   L(i)  d-chunks [128 tokens x 64 d] (K-major A operand)  -> logits / dA of all token tiles accumulate in TMEM
-//   P(i)  bricks  [64 tokens x 128 d] (the same swizzled bytes read as the MN-major A operand) -> pooled sums
+//   P(i)  bricks  [128 tokens x 128 d] (the same swizzled bytes read as the MN-major A operand) -> pooled sums
 // The second fetch finds the sample in L2 (148 CTAs x 526 KB = 78 MB of the 126 MB; first fetch evict_last, second
-// evict_first): measured with tools/dev_l2_probe.cu this order streams c2 at 108 us against 89 us for a single
-// pass and 2 x 89 us for two kernels.  Between the two phases nothing touches global memory: exp(S - max) (forward)
-// or dS (backward) go from the TMEM epilogue straight into shared memory as the UMMA B operand of the second phase.
-// To cover the epilogue's latency the first `lead` chunks of the NEXT sample are fetched and multiplied before the
-// pooled phase of the current one (double-buffered logit accumulators).
+// evict_first; tools/dev_l2_probe.cu: 108 us for c2 in this order against 89 us for a single pass and 2 x 89 us for
+// two kernels).  Between the phases nothing touches global memory: exp(S - max) (forward) or dS (backward) go from
+// the TMEM epilogue straight into shared memory as the UMMA B operand of the pooled phase.
 //
-// fp32 operands (queries, probabilities, dP, dS) are bf16 hi/lo pairs as in ep_pool_sm100.cu, but the pair is two
-// K-steps into ONE accumulator column (hi rows and lo rows are separate B operands) instead of two columns: the
-// accumulators need half the TMEM -- 2 x 96 (logits, double-buffered) + 256 (pooled, D = 1024) = 448 columns at
-// M = 32 -- which is what lets the whole sample live in one CTA.
+// Schedule.  HBM only stays busy if first fetches never stop, so the bricks of P(i) run CONCURRENTLY with the chunks of
+// L(i+1) (the first `lead` chunks may go ahead of the first brick and cover the softmax epilogue of sample i; after
+// that L(i+1) advances in step with P(i), which bounds the L2 footprint to one sample plus the lead per CTA).  That
+// needs the logit accumulators double-buffered, which decides the operand layouts:
+// fp32 operands (queries, probabilities, dP, dS) are bf16 hi/lo pairs as in ep_pool_sm100.cu; in the logit phase the
+// pair is two K-steps into ONE accumulator column (hi rows and lo rows are separate B operands): 2 x 96 columns at
+// N = 257, M = 32.  Forward pooled phase: hi and lo are separate columns of one N = 2 Mp MMA, D is walked in groups
+// of slices whose accumulators ping-pong between two TMEM buffers (2 x 2 slices x 64 columns), so a group drains
+// while the next accumulates.  Backward: the query gradient accumulates over the whole launch, all of D resident
+// (8 slices x 32 columns, hi/lo as two K-steps).  A tcgen05.mma with N <= 64 occupies the tensor core for 40-48
+// cycles whatever N (tools/dev_umma_probe.cu: 39/40/48/64/128 cycles at N = 16/32/64/128/256), so the MMA warp issues
+// from uniform registers with the whole warp converged.
 //
-// Warp roles (384 threads, one CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-11 epilogue (two per TMEM lane quadrant).
+// Pipeline bookkeeping is sized by what the primitives cost when issued from one thread (tools/dev_issue_probe.cu, SM
+// cycles): a TMA load 120-170, mbarrier.try_wait on a completed phase 170, tcgen05.commit 45.  With a barrier pair per
+// 16 KB slot one producer thread and the MMA warp each spent ~20 us per sample on these alone.  So there are two
+// rings with their own producer thread and few, large stages: the L ring holds whole d-chunks (query chunk + short
+// tail tile + the full token tiles, the tiles one TMA instruction), the P ring "tall bricks" [128 tokens x 128 d] (two
+// token blocks of a d-slice, one TMA instruction), and each ring has its own MMA-issuing warp, so that one warp's
+// barrier bookkeeping overlaps the other's MMAs (issue blocks while the tensor core's short queue is full).  The two
+// streams run independently; what orders them are monotonic progress counters in shared memory: the L warp starts
+// chunk c of sample i+1 only when the P warp has issued the matching share of sample i's bricks (beyond the first
+// `lead` chunks) and the epilogue has released the logit buffer.  The L producer also prefetches into L2 a few chunks
+// ahead (cp.async.bulk.prefetch.tensor), so that the two chunk stages shared memory has room for cover L2 latency.
+//
+// Warp roles (one CTA per SM): warp 0 L producer, warp 1 L MMA issuer, warp 2 TMEM allocator + P MMA issuer, warp 3 P
+// producer, warps 4.. epilogue (kEW warps, kEW / 4 per TMEM lane quadrant).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -35,20 +53,35 @@ using namespace ptx;
 
 namespace fused {
 constexpr int kSlotBytes = 16384;      // ring slot: [128 tokens x 64 d] chunk tile, or [64 tokens x 128 d] brick
-constexpr int kEpiWarpsF = 8;
-constexpr int kThreadsF = 32 * (4 + kEpiWarpsF);
-constexpr int kStatFloats = 2 * kEpiWarpsF * 64;   // per-warp partial max / sum of up to 64 queries
+constexpr int kEW = 16;                // epilogue warps
+constexpr int kSub = kEW / 4;          // ... per TMEM lane quadrant
+constexpr int kThreadsF = 32 * (4 + kEW);
+constexpr int kStatFloats = 2 * kEW * 64 + 128;   // per-warp partial max / sum of up to 64 queries + [2][64] row sums
+constexpr int kCache = 2;              // logit units a warp keeps in registers between the two softmax passes
+
+// developer trace (ep_set_debug bit 11): clock64 stamps of CTA 0's MMA warp and epilogue warp 4, 16 stamps x 8 samples
+__device__ long long g_trace[128];
+#define EP_TRACE(i, k) do { if (p.trace && blockIdx.x == 0 && (i) < 8 && lane == 0) g_trace[(i) * 16 + (k)] = clock64(); } while (0)
 
 struct FParams {
   int B, N, D, M, Mp;                  // Mp = M rounded up to 16: UMMA N, accumulator columns per tile / slice
   int ntiles, nfull, tail_rows;        // token tiles of 128; nfull of them loaded as full boxes; tail_rows > 0: the last
                                        // tile is a short box sharing its slot with the query chunk
-  int nchunks, nkb, nsl, nslots, lead, nbuf, bufcols, pcol0, tmem_cols, w_batched, qoff;
+  int nchunks, nkb, nsl, nL, nP, lbytes, lead, nbuf, bufcols, pcol0, tmem_cols, w_batched, qoff;   // nL/nP ring stages
+  int nkp, pf;                         // tall bricks per slice (= ceil(nkb / 2)); L2 prefetch distance in chunks
+  int nslg, G, pbufcols;               // pooled phase: G groups of <= nslg slices, accumulator buffers of pbufcols columns
+  int lsplit;                          // logit phase: 1 = hi/lo query rows as two K-steps into one column (N = Mp),
+                                       //              0 = as separate columns of one N = 2 Mp MMA (added in the epilogue)
+  int lcolw;                           // logit accumulator columns per token tile (Mp or 2 Mp)
+  int kl, last_rows;                   // k-steps (of 16 tokens) and token rows of the last tall brick of a slice
   float* S;                            // fwd: logits out (B, M, N);  bwd: saved logits in
   float* rmax; float* rsum;            // fwd: out;  bwd: in
   const float* delta;                  // bwd: (B, M)
   float* out;                          // fwd: P as bf16 hi/lo rows (B, M, 2, D) or fp32 (B, M, D);  bwd: partial dq [grid][M][D]
   int round_out;
+  int trace;
+  int noepi;                           // developer: epilogue warps only run the barrier protocol
+  int nomma;                           // developer: skip the MMA instructions (timing experiments; results are garbage)
 };
 
 __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
@@ -60,8 +93,14 @@ __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile.L2::cache_hint [%0, {%1, %2, %3}], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+               : "memory");
+}
+
 // 16 values per lane reduced over the 32 lanes of a warp in 16 shuffles (transposing butterfly): lane l ends with
-// value ((l >> 1) & 15 read as bits 16,8,4,2 -> 8,4,2,1) reduced over all lanes, replicated on 2 lanes.
+// value reduce16_index(l) reduced over all lanes, replicated on 2 lanes.
 template <bool kMax>
 __device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
   auto op = [](float a, float b) { return kMax ? fmaxf(a, b) : a + b; };
@@ -85,41 +124,53 @@ __device__ __forceinline__ uint32_t blk_off(uint32_t m, uint32_t t) {
   return m * 128u + (((t >> 3) ^ (m & 7u)) << 4) + (t & 7u) * 2u;
 }
 
+constexpr int kPBytes = 2 * kSlotBytes;   // P ring stage: a tall brick [128 tokens x 128 d] as two 64-d halves
+
 // kBwd = false: forward (logits, softmax, pooled tokens).  kBwd = true: backward (dA, dS, query gradient).
 template <bool kBwd>
 __global__ void __launch_bounds__(kThreadsF, 1)
-fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xt,
-             const __grid_constant__ CUtensorMap tm_xb, const __grid_constant__ CUtensorMap tm_w, const FParams p) {
-  // smem: [ring: nslots x 16 KB][operand blocks: nkb x (hi [Mp x 128 B], lo [Mp x 128 B])][stats][barriers]
+fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x1,
+             const __grid_constant__ CUtensorMap tm_xt, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bl,
+             const __grid_constant__ CUtensorMap tm_w, const FParams p) {
+  // smem: [L ring: nL x lbytes][P ring: nP x 32 KB][operand blocks: nkb x (hi [Mp x 128 B], lo [Mp x 128 B])][stats][barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (ring - smem_u32(smem_raw));
   const uint32_t half_bytes = (uint32_t)p.Mp * 128u;            // one hi or lo operand block
-  const uint32_t blk_base = ring + (uint32_t)p.nslots * kSlotBytes;
+  const uint32_t pring = ring + (uint32_t)(p.nL * p.lbytes);
+  const uint32_t blk_base = pring + (uint32_t)p.nP * kPBytes;
   const uint32_t blk_bytes = 2u * half_bytes * (uint32_t)p.nkb;
   const uint32_t stat_base = blk_base + blk_bytes;
   const uint32_t bar_base = stat_base + kStatFloats * 4u;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.nslots + s); };
-  const uint32_t misc = bar_base + 16u * p.nslots;
+  auto lfull_bar = [&](int s) { return bar_base + 8u * s; };              // L ring stage s loaded / consumed
+  auto lempty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto pfull_bar = [&](int s) { return bar_base + 64u + 8u * s; };         // P ring
+  auto pempty_bar = [&](int s) { return bar_base + 96u + 8u * s; };
+  const uint32_t misc = bar_base + 128u;
   auto tfull_bar = [&](int b) { return misc + 8u * b; };         // logit accumulators of buffer b complete
   const uint32_t eready_bar = misc + 16u;                         // operand blocks of the current sample written (and
-                                                                  // its logit accumulators read: the buffer is free)
-  const uint32_t pdone_bar = misc + 24u;                          // pooled MMAs of the current sample complete
-  const uint32_t pfree_bar = misc + 32u;                          // (fwd) pooled accumulators drained
-  const uint32_t tmem_slot = misc + 40u;
+                                                                  // its logit accumulators read: that buffer is free)
+  auto pdone_bar = [&](int b) { return misc + 24u + 8u * b; };   // pooled MMAs into accumulator buffer b complete
+  auto pfree_bar = [&](int b) { return misc + 40u + 8u * b; };   // (fwd) accumulator buffer b drained
+  const uint32_t tmem_slot = misc + 56u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - ring));
+  // monotonic progress counters (written by one thread, polled by another): tall bricks issued by the P warp, samples
+  // whose logit accumulators the epilogue has finished reading
+  volatile int* p_issued = reinterpret_cast<volatile int*>(gen + (misc + 64u - ring));
+  volatile int* e_done = reinterpret_cast<volatile int*>(gen + (misc + 68u - ring));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nslots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int q = 0; q < 4; ++q) { mbar_init(lfull_bar(q), 1); mbar_init(lempty_bar(q), 1); mbar_init(pfull_bar(q), 1); mbar_init(pempty_bar(q), 1); }
     for (int b = 0; b < 2; ++b) mbar_init(tfull_bar(b), 1);
-    mbar_init(eready_bar, kEpiWarpsF);
-    mbar_init(pdone_bar, 1);
-    mbar_init(pfree_bar, kEpiWarpsF);
+    mbar_init(eready_bar, kEW);
+    for (int b = 0; b < 2; ++b) { mbar_init(pdone_bar(b), 1); mbar_init(pfree_bar(b), kEW); }
+    *p_issued = 0;
+    *e_done = 0;
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_xt); prefetch_tmap(&tm_xb); prefetch_tmap(&tm_w); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_x1); prefetch_tmap(&tm_xt); prefetch_tmap(&tm_w); }
+  if (warp == 3 && lane == 0) { prefetch_tmap(&tm_b); prefetch_tmap(&tm_bl); }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   // operand blocks start as zeros: rows m >= M and tokens that no epilogue thread owns stay zero for the whole launch
   for (uint32_t o = threadIdx.x * 16u; o < blk_bytes; o += kThreadsF * 16u)
@@ -134,197 +185,253 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   const uint32_t w_bytes = 2u * half_bytes;                       // query / dP chunk: hi rows then lo rows
   const bool mixed_tail = p.tail_rows > 0;                        // the short last tile shares the query chunk's slot
 
+  // tiles of a chunk are loaded by boxes of up to 256 token rows
+  const int tile_rows = p.nfull * 128;
+
   if (warp == 0) {
+    // ---- L producer: chunk after chunk, sample after sample, into the L ring; stage = [slot 0: short tail tile at 0,
+    // query chunk at qoff][nfull x 16 KB token tiles]
     if (lane == 0 && nmine > 0) {
-      const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+      const uint64_t pol_last = policy_evict_last();
+      const uint32_t tx = w_bytes + (mixed_tail ? (uint32_t)p.tail_rows * 128u : 0u) + (uint32_t)p.nfull * kSlotBytes;
       int s = 0;
       uint32_t ph = 0;
-      auto acquire = [&]() -> uint32_t {
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        return ring + (uint32_t)s * kSlotBytes;
-      };
-      auto advance = [&]() { if (++s == p.nslots) { s = 0; ph ^= 1u; } };
-      // L: chunk c of sample b = [query chunk (+ short tail tile)] slot, then one slot per full token tile
-      auto load_L = [&](int b, int c0, int c1) {
-        for (int c = c0; c < c1; ++c) {
-          uint32_t dst = acquire();
-          mbar_arrive_expect_tx(full_bar(s), w_bytes + (mixed_tail ? (uint32_t)p.tail_rows * 128u : 0u));
-          tma_load_4d_hint(dst + (uint32_t)p.qoff, &tm_w, full_bar(s), c * 64, 0, 0, p.w_batched ? b : 0, pol_last);
-          tma_load_4d_hint(dst + (uint32_t)p.qoff + half_bytes, &tm_w, full_bar(s), c * 64, 1, 0, p.w_batched ? b : 0, pol_last);
-          if (mixed_tail) tma_load_3d_hint(dst, &tm_xt, full_bar(s), c * 64, p.nfull * 128, b, pol_last);
-          advance();
-          for (int t = 0; t < p.nfull; ++t) {
-            dst = acquire();
-            mbar_arrive_expect_tx(full_bar(s), kSlotBytes);
-            tma_load_3d_hint(dst, &tm_x, full_bar(s), c * 64, t * 128, b, pol_last);
-            advance();
-          }
-        }
-      };
-      auto load_P = [&](int b) {
-        for (int kb = 0; kb < p.nkb; ++kb)
-          for (int sl = 0; sl < p.nsl; ++sl) {
-            const uint32_t dst = acquire();
-            mbar_arrive_expect_tx(full_bar(s), kSlotBytes);
-            tma_load_3d_hint(dst, &tm_xb, full_bar(s), sl * 128, kb * 64, b, pol_first);
-            tma_load_3d_hint(dst + kSlotBytes / 2, &tm_xb, full_bar(s), sl * 128 + 64, kb * 64, b, pol_first);
-            advance();
-          }
-      };
-      load_L(blockIdx.x, 0, p.nchunks);
+      long long t_wait = 0, t_begin = clock64();
       for (int i = 0; i < nmine; ++i) {
         const int b = blockIdx.x + i * gridDim.x;
-        if (i + 1 < nmine) load_L(b + gridDim.x, 0, p.lead);
-        load_P(b);
-        if (i + 1 < nmine) load_L(b + gridDim.x, p.lead, p.nchunks);
+        const int zb = p.w_batched ? b : 0;
+        for (int c = 0; c < p.nchunks; ++c) {
+          const long long t0 = p.trace ? clock64() : 0;
+          mbar_wait(lempty_bar(s), ph ^ 1u);
+          if (p.trace) t_wait += clock64() - t0;
+          const uint32_t bar = lfull_bar(s), dst = ring + (uint32_t)(s * p.lbytes);
+          mbar_arrive_expect_tx(bar, tx);
+          for (int r = 0; r < tile_rows; r += 256)                 // two tiles per instruction, a last odd one alone
+            tma_load_3d_hint(dst + kSlotBytes + (uint32_t)r * 128u, tile_rows - r >= 256 ? &tm_x : &tm_x1, bar, c * 64, r, b, pol_last);
+          tma_load_4d_hint(dst + (uint32_t)p.qoff, &tm_w, bar, c * 64, 0, 0, zb, pol_last);
+          tma_load_4d_hint(dst + (uint32_t)p.qoff + half_bytes, &tm_w, bar, c * 64, 1, 0, zb, pol_last);
+          if (mixed_tail) tma_load_3d_hint(dst, &tm_xt, bar, c * 64, tile_rows, b, pol_last);
+          if (p.pf > 0) {                                          // the chunk pf ahead (maybe of the next sample) -> L2
+            int cp = c + p.pf, bp = b;
+            if (cp >= p.nchunks) { cp -= p.nchunks; bp += gridDim.x; }
+            if (bp < p.B) {
+              for (int r = 0; r < tile_rows; r += 256) tma_prefetch_3d(tile_rows - r >= 256 ? &tm_x : &tm_x1, cp * 64, r, bp, pol_last);
+              if (mixed_tail) tma_prefetch_3d(&tm_xt, cp * 64, tile_rows, bp, pol_last);
+            }
+          }
+          if (++s == p.nL) { s = 0; ph ^= 1u; }
+        }
       }
+      if (p.trace && blockIdx.x == 0) { g_trace[120] = t_wait; g_trace[121] = clock64() - t_begin; }   // L producer: ring-full wait, total
     }
-  } else if (warp == 1) {
-    // MMA issue.  The whole warp walks the schedule (uniform control flow, descriptors in uniform registers) and one
-    // elected lane issues: a tcgen05.mma with N <= 64 occupies the tensor core for only ~40-48 cycles
-    // (tools/dev_umma_probe.cu), so per-instruction address arithmetic in a single divergent thread would be the limit.
-    if (nmine > 0) {
-      const bool leader = elect_one();
-      const uint32_t idesc_L = idesc_bf16(128, 2 * p.Mp, 0, 0);   // logits: N = hi rows + lo rows of the query chunk
-      const uint32_t idesc_P = idesc_bf16(128, p.Mp, 1, 0);       // pooled: A (tokens as K) is MN-major
-      const uint64_t dK = smem_desc_sw128(0, 16, 1024);           // + (address >> 4)
-      const uint64_t dMN = smem_desc_sw128(0, kSlotBytes / 2, 1024);
-      const uint32_t ncolL = 2u * (uint32_t)p.Mp;
+  } else if (warp == 3) {
+    // ---- P producer: the tall bricks of sample after sample, slice after slice (the MMA warp's group order is slice
+    // order), into the P ring
+    if (lane == 0 && nmine > 0) {
+      const uint64_t pol_first = policy_evict_first();
+      const uint32_t last_bytes = (uint32_t)p.last_rows * 256u;
       int s = 0;
       uint32_t ph = 0;
-      auto advance = [&]() { if (++s == p.nslots) { s = 0; ph ^= 1u; } };
-      // logits of sample ordinal j, chunks [c0, c1), into accumulator buffer j % nbuf
-      auto mma_L = [&](int j, int c0, int c1) {
-        const uint32_t acc = tmem_base + (uint32_t)((j % p.nbuf) * p.bufcols);
-        for (int c = c0; c < c1; ++c) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const int ws = s;
-          const uint32_t wslot = ring + (uint32_t)s * kSlotBytes;
-          const uint64_t bd = dK + (uint64_t)((wslot + (uint32_t)p.qoff) >> 4);
-          advance();
-          for (int t = 0; t < p.nfull; ++t) {
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint64_t ad = dK + (uint64_t)((ring + (uint32_t)s * kSlotBytes) >> 4);
-            if (leader) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(acc + (uint32_t)t * ncolL, ad + 2u * k, bd + 2u * k, idesc_L, (uint32_t)((c | k) != 0));
-              umma_commit(empty_bar(s));
-            }
-            __syncwarp();
-            advance();
-          }
-          if (leader) {
-            if (mixed_tail) {
-              const uint64_t ad = dK + (uint64_t)(wslot >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(acc + (uint32_t)p.nfull * ncolL, ad + 2u * k, bd + 2u * k, idesc_L, (uint32_t)((c | k) != 0));
-            }
-            umma_commit(empty_bar(ws));
-          }
-          __syncwarp();
-        }
-      };
-      mma_L(0, 0, p.nchunks);
-      if (leader) umma_commit(tfull_bar(0));
-      __syncwarp();
-      const uint32_t pacc = tmem_base + (uint32_t)p.pcol0;
+      long long t_wait = 0, t_begin = clock64();
       for (int i = 0; i < nmine; ++i) {
-        const int j = i + 1;
-        // (lead > 0 needs nbuf == 2: buffer j % 2 was read by the epilogue of sample j - 2, which finished before
-        //  eready of sample j - 2 completed -- waited for two iterations ago)
-        if (j < nmine && p.lead > 0) mma_L(j, 0, p.lead);
-        mbar_wait(eready_bar, (uint32_t)(i & 1));                  // operand blocks of sample i are in shared memory
-        if (!kBwd) mbar_wait(pfree_bar, ((uint32_t)(i & 1)) ^ 1u); // pooled accumulators of sample i - 1 drained
-        tc_fence_after();
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const uint64_t bd_hi = dK + (uint64_t)((blk_base + (uint32_t)kb * 2u * half_bytes) >> 4);
-          const uint64_t bd_lo = bd_hi + (uint64_t)(half_bytes >> 4);
-          for (int sl = 0; sl < p.nsl; ++sl) {
-            mbar_wait(full_bar(s), ph);
+        const int b = blockIdx.x + i * gridDim.x;
+        for (int sl = 0; sl < p.nsl; ++sl)
+          for (int kp = 0; kp < p.nkp; ++kp) {
+            const long long t0 = p.trace ? clock64() : 0;
+            mbar_wait(pempty_bar(s), ph ^ 1u);
+            if (p.trace) t_wait += clock64() - t0;
+            const bool last = kp == p.nkp - 1 && p.last_rows < 128;
+            mbar_arrive_expect_tx(pfull_bar(s), last ? last_bytes : (uint32_t)kPBytes);
+            tma_load_4d_hint(pring + (uint32_t)s * kPBytes, last ? &tm_bl : &tm_b, pfull_bar(s), 0, kp * 128, 2 * sl, b, pol_first);
+            if (++s == p.nP) { s = 0; ph ^= 1u; }
+          }
+      }
+      if (p.trace && blockIdx.x == 0) { g_trace[125] = t_wait; g_trace[126] = clock64() - t_begin; }   // P producer
+    }
+  } else if (warp == 1) {
+    // ---- L MMA issue: the whole warp walks the chunks (uniform control flow, descriptors in uniform registers), one
+    // elected lane issues
+    if (nmine > 0) {
+      const bool leader = elect_one();
+      const uint32_t idesc_L = idesc_bf16(128, p.lsplit ? p.Mp : 2 * p.Mp, 0, 0);
+      const uint64_t dK = smem_desc_sw128(0, 16, 1024);           // + (address >> 4)
+      const uint64_t lo_off = (uint64_t)(half_bytes >> 4);
+      const int nst = p.nsl * p.nkp;                               // tall bricks per sample
+      int ls = 0;
+      uint32_t lph = 0;
+      long long t_wait = 0, t_gate = 0, t_begin = clock64();
+      for (int j = 0; j < nmine; ++j) {
+        const uint32_t acc = tmem_base + (uint32_t)((j % p.nbuf) * p.bufcols);
+        for (int c = 0; c < p.nchunks; ++c) {
+          // order against the other stream: the logit buffer is free (its previous sample's epilogue has read it), and
+          // chunk c runs at most `lead` chunks ahead of the matching share of the previous sample's bricks
+          const long long tg = p.trace ? clock64() : 0;
+          if (c == 0 && j >= p.nbuf) {
+            while (*e_done < j - p.nbuf + 1) {}
             tc_fence_after();
-            const uint64_t ad = dMN + (uint64_t)((ring + (uint32_t)s * kSlotBytes) >> 4);
-            if (leader) {
+          }
+          if (j > 0) {
+            const int need = c < p.lead ? (j - 1) * nst : (j - 1) * nst + (c - p.lead + 1) * nst / (p.nchunks - p.lead);
+            while (*p_issued < need) {}
+          }
+          if (p.trace) t_gate += clock64() - tg;
+          const long long t0 = p.trace ? clock64() : 0;
+          mbar_wait(lfull_bar(ls), lph);
+          if (p.trace) t_wait += clock64() - t0;
+          const uint32_t st0 = ring + (uint32_t)(ls * p.lbytes);
+          const uint64_t bd = dK + (uint64_t)((st0 + (uint32_t)p.qoff) >> 4);
+          if (leader && !p.nomma) {
+            for (int t = 0; t < p.ntiles; ++t) {
+              // full tiles follow slot 0, the short tail tile sits at its start
+              const uint64_t ad = dK + (uint64_t)((t < p.nfull ? st0 + (uint32_t)(1 + t) * kSlotBytes : st0) >> 4);
+              const uint32_t d = acc + (uint32_t)(t * p.lcolw);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t first = kBwd ? (uint32_t)((i | kb | k) != 0) : (uint32_t)((kb | k) != 0);
-                umma_f16(pacc + (uint32_t)(sl * p.Mp), ad + 128u * k, bd_hi + 2u * k, idesc_P, first);
-                umma_f16(pacc + (uint32_t)(sl * p.Mp), ad + 128u * k, bd_lo + 2u * k, idesc_P, 1u);
+                umma_f16(d, ad + 2u * k, bd + 2u * k, idesc_L, (uint32_t)((c | k) != 0));
+                if (p.lsplit) umma_f16(d, ad + 2u * k, bd + lo_off + 2u * k, idesc_L, 1u);
               }
-              umma_commit(empty_bar(s));
             }
-            __syncwarp();
-            advance();
           }
+          if (leader) umma_commit(lempty_bar(ls));
+          __syncwarp();
+          if (++ls == p.nL) { ls = 0; lph ^= 1u; }
         }
-        if (leader) umma_commit(pdone_bar);
+        if (leader) umma_commit(tfull_bar(j % p.nbuf));
         __syncwarp();
-        if (j < nmine) {
-          mma_L(j, p.lead, p.nchunks);
-          if (leader) umma_commit(tfull_bar(j % p.nbuf));
+        EP_TRACE(j, 2);                                            // L warp: logits of sample j issued
+      }
+      if (p.trace && blockIdx.x == 0 && lane == 0) {               // L warp: load-starved wait, ordering wait, total
+        g_trace[122] = t_wait; g_trace[123] = t_gate; g_trace[124] = clock64() - t_begin;
+      }
+    }
+  } else if (warp == 2) {
+    // ---- P MMA issue (this warp also owns the TMEM allocation)
+    if (nmine > 0) {
+      const bool leader = elect_one();
+      const uint32_t idesc_P = idesc_bf16(128, kBwd ? p.Mp : 2 * p.Mp, 1, 0);   // pooled: A (tokens as K) is MN-major
+      const uint64_t dK = smem_desc_sw128(0, 16, 1024);
+      const uint64_t dMN = smem_desc_sw128(0, kPBytes / 2, 1024);  // halves of a tall brick are 128 rows apart
+      const uint64_t dMN_last = smem_desc_sw128(0, (uint32_t)p.last_rows * 128u, 1024);
+      const uint64_t lo_off = (uint64_t)(half_bytes >> 4);
+      const uint32_t pcolw = kBwd ? (uint32_t)p.Mp : 2u * (uint32_t)p.Mp;      // accumulator columns per slice
+      int ps = 0, issued = 0;
+      uint32_t pph = 0;
+      long long t_wait = 0, t_gate = 0, t_begin = clock64();
+      for (int i = 0; i < nmine; ++i) {
+        EP_TRACE(i, 0);                                            // P warp: start waiting for the operand blocks
+        const long long tg = p.trace ? clock64() : 0;
+        mbar_wait(eready_bar, (uint32_t)(i & 1));                  // operand blocks of sample i are in shared memory
+        tc_fence_after();
+        if (p.trace) t_gate += clock64() - tg;
+        EP_TRACE(i, 1);                                            // P warp: pooled phase starts
+        for (int g = 0; g < p.G; ++g) {
+          const int gg = kBwd ? 2 * i : i * p.G + g;               // bwd: one group per sample, always buffer 0
+          if (!kBwd) {                                             // this buffer's previous group has been drained
+            mbar_wait(pfree_bar(gg & 1), (((uint32_t)(gg >> 1)) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          const int gs = min(p.nslg, p.nsl - g * p.nslg);
+          for (int slg = 0; slg < gs; ++slg) {
+            const uint32_t pacc = tmem_base + (uint32_t)p.pcol0 + (kBwd ? 0u : (uint32_t)((gg & 1) * p.pbufcols)) + (uint32_t)slg * pcolw;
+            for (int kp = 0; kp < p.nkp; ++kp) {
+              const long long t0 = p.trace ? clock64() : 0;
+              mbar_wait(pfull_bar(ps), pph);
+              if (p.trace) t_wait += clock64() - t0;
+              const bool last = kp == p.nkp - 1 && p.last_rows < 128;
+              const int ks = last ? p.kl : 8;
+              const uint64_t ad = (last ? dMN_last : dMN) + (uint64_t)((pring + (uint32_t)ps * kPBytes) >> 4);
+              const uint64_t bd0 = dK + (uint64_t)((blk_base + (uint32_t)(2 * kp) * 2u * half_bytes) >> 4);
+              if (leader && !p.nomma) {
+                for (int k = 0; k < ks; ++k) {
+                  const uint64_t bd = bd0 + (uint64_t)((k >> 2) * (2u * half_bytes >> 4)) + 2u * (k & 3);
+                  if (kBwd) {
+                    umma_f16(pacc, ad + 128u * k, bd, idesc_P, (uint32_t)((i | kp | k) != 0));
+                    umma_f16(pacc, ad + 128u * k, bd + lo_off, idesc_P, 1u);
+                  } else {
+                    umma_f16(pacc, ad + 128u * k, bd, idesc_P, (uint32_t)((kp | k) != 0));
+                  }
+                }
+              }
+              ++issued;
+              if (leader) { umma_commit(pempty_bar(ps)); *p_issued = issued; }
+              __syncwarp();
+              if (++ps == p.nP) { ps = 0; pph ^= 1u; }
+            }
+          }
+          if (leader) umma_commit(pdone_bar(gg & 1));
           __syncwarp();
         }
+        EP_TRACE(i, 3);                                            // P warp: sample i pooled
+      }
+      if (p.trace && blockIdx.x == 0 && lane == 0) {               // P warp: load-starved wait, operand-block wait, total
+        g_trace[117] = t_wait; g_trace[118] = t_gate; g_trace[119] = clock64() - t_begin;
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4, wq = ew & 3, eh = ew >> 2;
+    const int ew = warp - 4, wq = ew & 3, es = ew >> 2;            // quadrant, sub-warp within the quadrant
     const int upt = p.Mp >> 4;                                     // 16-query units per tile / slice
-    float* pmax = reinterpret_cast<float*>(gen + (stat_base - ring));   // [8][64]
-    float* psum = pmax + kEpiWarpsF * 64;                               // [8][64]
+    float* pmax = reinterpret_cast<float*>(gen + (stat_base - ring));   // [kEW][64]
+    float* psum = pmax + kEW * 64;                                      // [kEW][64]
+    float* tot = psum + kEW * 64;                                       // [2][64] softmax row sums, by sample parity
     uint8_t* blk_gen = gen + (blk_base - ring);
     const int ridx = reduce16_index(lane);
     const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
     const int nunits = p.ntiles * upt;
 
-    // pooled accumulators -> global (fwd: normalised P of sample b; bwd: this CTA's partial dq)
-    auto drain = [&](int b) {
-      const uint32_t acc = tmem_base + lane_base + (uint32_t)p.pcol0;
+    // fwd: group g of sample ordinal i (accumulator buffer gg & 1) -> normalised P rows in global memory
+    auto drain_group = [&](int b, int i, int g) {
+      const int gg = i * p.G + g;
+      mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + lane_base + (uint32_t)(p.pcol0 + (gg & 1) * p.pbufcols);
+      const int gs = min(p.nslg, p.nsl - g * p.nslg);
       float invl[2] = {1.f, 1.f};                                  // lane l keeps 1/rowsum of queries l and 32 + l
-      if (!kBwd) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          if (h * 32 + lane < p.M) invl[h] = 1.f / psum[h * 32 + lane];      // row sums of this sample (table row 0 = totals)
-      }
-      for (int u = eh; u < p.nsl * upt; u += 2) {
-        const int sl = u / upt, j0 = (u - sl * upt) << 4;
-        const int d = sl * 128 + wq * 32 + lane;
-        uint32_t r[16];
-        tmem_ld16(acc + (uint32_t)(sl * p.Mp + j0), r);
+      for (int h = 0; h < 2; ++h)
+        if (h * 32 + lane < p.M) invl[h] = 1.f / tot[(i & 1) * 64 + h * 32 + lane];
+      for (int u = es; u < gs * upt; u += kSub) {
+        const int slg = u / upt, j0 = (u - slg * upt) << 4;
+        const int d = (g * p.nslg + slg) * 128 + wq * 32 + lane;
+        uint32_t rh[16], rl[16];
+        tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + j0), rh);
+        tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + p.Mp + j0), rl);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int m = j0 + i;                                    // warp-uniform
+        for (int q = 0; q < 16; ++q) {
+          const int m = j0 + q;                                    // warp-uniform
           if (m < p.M) {
-            float v = __uint_as_float(r[i]);
-            if (!kBwd) {
-              v *= __shfl_sync(0xffffffffu, m < 32 ? invl[0] : invl[1], m & 31);
-              if (p.round_out) {                                   // P as bf16 hi/lo rows (b, m, {hi, lo}, d)
-                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-                __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
-                pr[0] = hi;
-                pr[p.D] = lo;
-              } else {
-                p.out[((size_t)b * p.M + m) * p.D + d] = v;
-              }
+            const float v = (__uint_as_float(rh[q]) + __uint_as_float(rl[q])) *
+                            __shfl_sync(0xffffffffu, m < 32 ? invl[0] : invl[1], m & 31);
+            if (p.round_out) {                                     // P as bf16 hi/lo rows (b, m, {hi, lo}, d)
+              const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+              const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+              __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
+              pr[0] = hi;
+              pr[p.D] = lo;
             } else {
-              p.out[((size_t)blockIdx.x * p.M + m) * p.D + d] = v;
+              p.out[((size_t)b * p.M + m) * p.D + d] = v;
             }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfree_bar(gg & 1));
     };
-    // logits (hi column + lo column) of unit u = (tile, 16 queries) for this lane's token
     auto load_unit = [&](uint32_t acc, int t, int j0, float (&v)[16]) {
-      uint32_t rh[16], rl[16];
-      tmem_ld16(acc + (uint32_t)(t * 2 * p.Mp + j0), rh);
-      tmem_ld16(acc + (uint32_t)(t * 2 * p.Mp + p.Mp + j0), rl);
-      tmem_ld_wait();
+      uint32_t r[16];
+      tmem_ld16(acc + (uint32_t)(t * p.lcolw + j0), r);
+      if (p.lsplit) {
+        tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rh[q]) + __uint_as_float(rl[q]);
+        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+      } else {                                                     // hi and lo query rows are separate columns
+        uint32_t r2[16];
+        tmem_ld16(acc + (uint32_t)(t * p.lcolw + p.Mp + j0), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]) + __uint_as_float(r2[q]);
+      }
     };
     auto store_hilo = [&](uint8_t* blk, int m, int tt, float e) {
       const __nv_bfloat16 hi = __float2bfloat16_rn(e);
@@ -336,16 +443,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     for (int i = 0; i < nmine; ++i) {
       const int b = blockIdx.x + i * gridDim.x;
       const int buf = i % p.nbuf;
-      if (i > 0) {                                                 // pooled MMAs of sample i - 1 complete: blocks reusable
-        mbar_wait(pdone_bar, (uint32_t)((i - 1) & 1));
-        tc_fence_after();
-        if (!kBwd) {
-          drain(b - gridDim.x);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pfree_bar);
-        }
-      }
+      if (warp == 4) EP_TRACE(i, 8);                               // epilogue: sample i begins
       // bwd: lane l keeps the row statistics of queries l and 32 + l of this sample
       float st_mx[2] = {0.f, 0.f}, st_inv[2] = {0.f, 0.f}, st_dl[2] = {0.f, 0.f};
       if (kBwd) {
@@ -362,19 +460,19 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       }
       mbar_wait(tfull_bar(buf), ((uint32_t)(i / p.nbuf)) & 1u);
       tc_fence_after();
+      if (warp == 4) EP_TRACE(i, 9);                               // epilogue: logits complete
       const uint32_t acc = tmem_base + lane_base + (uint32_t)(buf * p.bufcols);
+      float cache[kCache][16];
 
-      if (!kBwd) {
+      if (!kBwd && !p.noepi) {
         // ---- pass 1: per-query maximum over the tokens (per-warp partial rows, combined in a fixed order); the
         // first kCache units of a warp stay in registers for pass 2
-        constexpr int kCache = 3;
-        float cache[kCache][16];
         pmax[ew * 64 + lane] = -INFINITY;
         pmax[ew * 64 + 32 + lane] = -INFINITY;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < kCache; ++k) {
-          const int u = eh + 2 * k;
+          const int u = es + kSub * k;
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (u < nunits && t * 128 + wq * 32 < p.N) {             // (warp-uniform) some lane of this warp holds a token
             load_unit(acc, t, j0, cache[k]);
@@ -389,7 +487,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             __syncwarp();
           }
         }
-        for (int u = eh + 2 * kCache; u < nunits; u += 2) {
+        for (int u = es + kSub * kCache; u < nunits; u += kSub) {
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
@@ -403,14 +501,31 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           }
           __syncwarp();
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarpsF) : "memory");
+      }
+      if (i > 0) {                                                 // every pooled MMA of sample i - 1 complete: blocks reusable
+        const int gl = kBwd ? 2 * (i - 1) : i * p.G - 1;           // its last group
+        mbar_wait(pdone_bar(gl & 1), ((uint32_t)(gl >> 1)) & 1u);
+        tc_fence_after();
+        if (warp == 4) EP_TRACE(i, 10);                            // epilogue: pooled MMAs of sample i - 1 complete
+      }
+      if (p.noepi) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(eready_bar);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
+        if (ew == 0 && lane == 0) *e_done = i + 1;
+        if (!kBwd) {
+          if (i > 0) { const int gg = i * p.G - 1; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
+          for (int g = 0; g + 1 < p.G; ++g) { const int gg = i * p.G + g; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
+        }
+      } else if (!kBwd) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
         float mx_lo = -INFINITY, mx_hi = -INFINITY;                // lane l: queries l and 32 + l
 #pragma unroll
-        for (int w = 0; w < kEpiWarpsF; ++w) {
+        for (int w = 0; w < kEW; ++w) {
           mx_lo = fmaxf(mx_lo, pmax[w * 64 + lane]);
           mx_hi = fmaxf(mx_hi, pmax[w * 64 + 32 + lane]);
         }
-        // (every warp's drain of sample i - 1 -- the last reader of the totals in psum row 0 -- precedes the barrier above)
         psum[ew * 64 + lane] = 0.f;
         psum[ew * 64 + 32 + lane] = 0.f;
         __syncwarp();
@@ -437,11 +552,11 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         };
 #pragma unroll
         for (int k = 0; k < kCache; ++k) {
-          const int u = eh + 2 * k;
+          const int u = es + kSub * k;
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (u < nunits && t * 128 + wq * 32 < p.N) emit(t, j0, cache[k]);
         }
-        for (int u = eh + 2 * kCache; u < nunits; u += 2) {
+        for (int u = es + kSub * kCache; u < nunits; u += kSub) {
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
@@ -452,26 +567,33 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(eready_bar);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarpsF) : "memory");
-        // totals into row 0 of psum (read by the next drain) and the saved statistics
+        if (warp == 4) EP_TRACE(i, 12);                            // epilogue: operand blocks written
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
+        if (ew == 0 && lane == 0) *e_done = i + 1;                 // every warp has read the logit accumulators of sample i
+        // row sums of this sample (for its drains) and the saved statistics
         if (ew == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int m = 32 * h + lane;
             float su = 0.f;
 #pragma unroll
-            for (int w = 0; w < kEpiWarpsF; ++w) su += psum[w * 64 + m];
-            psum[m] = su;
+            for (int w = 0; w < kEW; ++w) su += psum[w * 64 + m];
+            tot[(i & 1) * 64 + m] = su;
             if (m < p.M) {
               p.rmax[(size_t)b * p.M + m] = h ? mx_hi : mx_lo;
               p.rsum[(size_t)b * p.M + m] = su;
             }
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarpsF) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
+        // drains: the last group of the previous sample, then this sample's groups but the last (which completes
+        // together with the next sample's logits)
+        if (i > 0) drain_group(b - gridDim.x, i - 1, p.G - 1);
+        for (int g = 0; g + 1 < p.G; ++g) drain_group(b, i, g);
+        if (warp == 4) EP_TRACE(i, 13);                            // epilogue: drains done
       } else {
         // ---- backward: dS = A (dA - delta), A recomputed from the saved logits and row statistics
-        for (int u = eh; u < nunits; u += 2) {
+        for (int u = es; u < nunits; u += kSub) {
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           const int n = t * 128 + wq * 32 + lane;
@@ -503,15 +625,32 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(eready_bar);
+        if (warp == 4) EP_TRACE(i, 12);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
+        if (ew == 0 && lane == 0) *e_done = i + 1;                 // every warp has read the dA accumulators of sample i
       }
     }
-    if (nmine > 0) {
-      mbar_wait(pdone_bar, (uint32_t)((nmine - 1) & 1));
+    if (nmine > 0 && !kBwd) {
+      drain_group(blockIdx.x + (nmine - 1) * gridDim.x, nmine - 1, p.G - 1);
+    } else if (nmine > 0) {
+      // bwd: the query-gradient partial of this CTA, all slices
+      const int gl = 2 * (nmine - 1);
+      mbar_wait(pdone_bar(0), ((uint32_t)(gl >> 1)) & 1u);
       tc_fence_after();
-      drain(blockIdx.x + (nmine - 1) * gridDim.x);
+      const uint32_t acc = tmem_base + lane_base + (uint32_t)p.pcol0;
+      for (int u = es; u < p.nsl * upt; u += kSub) {
+        const int sl = u / upt, j0 = (u - sl * upt) << 4;
+        const int d = sl * 128 + wq * 32 + lane;
+        uint32_t r[16];
+        tmem_ld16(acc + (uint32_t)(sl * p.Mp + j0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (j0 + q < p.M) p.out[((size_t)blockIdx.x * p.M + j0 + q) * p.D + d] = __uint_as_float(r[q]);
+      }
     } else if (kBwd) {
       // a CTA without samples still owns a partial-gradient slice: zeros
-      for (size_t o = (size_t)(warp - 4) * 32 + lane; o < (size_t)p.M * p.D; o += 32 * kEpiWarpsF)
+      for (size_t o = (size_t)(warp - 4) * 32 + lane; o < (size_t)p.M * p.D; o += 32 * kEW)
         p.out[(size_t)blockIdx.x * p.M * p.D + o] = 0.f;
     }
   }
@@ -525,14 +664,15 @@ int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 
 struct FPlan {
   bool ok = false;
-  int Mp, ntiles, nfull, tail_rows, nchunks, nkb, nsl, nslots, lead, nbuf, bufcols, pcol0, tmem_cols, qoff;
+  int Mp, ntiles, nfull, tail_rows, nchunks, nkb, nsl, nL, nP, lbytes, nkp, pf, lead, nbuf, bufcols, pcol0, tmem_cols, qoff, nslg, G, pbufcols;
+  int lsplit, lcolw, kl, last_rows;
   size_t smem;
 };
 
 // L2 budget for the samples in flight (every CTA holds one sample plus the lead of the next between its two fetches)
 constexpr size_t kL2Budget = 100ull << 20;
 
-FPlan make_fplan(int N, int D, int M, int ctas) {
+FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   FPlan pl;
   if (D % 128 != 0 || M < 1 || M > 64 || N < 1) return pl;
   pl.Mp = round16(M);
@@ -546,22 +686,50 @@ FPlan make_fplan(int N, int D, int M, int ctas) {
   pl.nchunks = D / 64;
   pl.nkb = (N + 63) / 64;
   pl.nsl = D / 128;
-  // TMEM: logit accumulators (hi and lo query rows are separate columns: ntiles x 2 Mp), double-buffered when
-  // they fit twice beside the pooled accumulators (hi/lo operand blocks are two K-steps into ONE column: nsl x Mp)
-  pl.bufcols = pl.ntiles * 2 * pl.Mp;
-  pl.nbuf = (2 * pl.bufcols + pl.nsl * pl.Mp <= 512) ? 2 : 1;
+  pl.nkp = (pl.nkb + 1) / 2;                                      // tall bricks (128 tokens) per d-slice
+  pl.kl = (N - (pl.nkp - 1) * 128 + 15) / 16;                     // 16-token k-steps of the last tall brick
+  pl.last_rows = pl.kl * 16;
+  // TMEM plan.  Logit accumulators per token tile: 2 Mp columns (hi and lo query rows side by side: one MMA per
+  // k-step, half the shared-memory operand reads) or Mp (two K-steps into one column); one or two buffers.  Pooled
+  // accumulators: backward all slices resident (nsl x Mp, hi/lo as K-steps), forward two ping-pong buffers of nslg
+  // slices x 2 Mp columns.  Preference: two logit buffers (the next sample's first chunks overlap the softmax), then
+  // side-by-side columns.
+  const int force = (g_debug >> 20) & 3;                          // dev knob: 1 = one logit buffer, 2 = K-split logits
+  pl.nbuf = 0;
+  for (int cand = 0; cand < 4 && !pl.nbuf; ++cand) {
+    const int nbuf = cand < 2 ? 2 : 1, lsplit = cand & 1;
+    if ((force == 1 && nbuf == 2) || (force == 2 && !lsplit)) continue;
+    const int lcolw = lsplit ? pl.Mp : 2 * pl.Mp;
+    const int left = 512 - nbuf * pl.ntiles * lcolw;
+    if (bwd) {
+      if (left < pl.nsl * pl.Mp) continue;
+      pl.nslg = pl.nsl; pl.G = 1; pl.pbufcols = pl.nsl * pl.Mp;
+    } else {
+      if (left < 2 * 2 * pl.Mp) continue;
+      pl.nslg = std::min(pl.nsl, left / (2 * 2 * pl.Mp));
+      pl.G = (pl.nsl + pl.nslg - 1) / pl.nslg;
+      pl.nslg = (pl.nsl + pl.G - 1) / pl.G;                       // balance the groups
+      pl.pbufcols = pl.nslg * 2 * pl.Mp;
+    }
+    pl.nbuf = nbuf; pl.lsplit = lsplit; pl.lcolw = lcolw;
+  }
+  if (!pl.nbuf) return pl;
+  pl.bufcols = pl.ntiles * pl.lcolw;
   pl.pcol0 = pl.nbuf * pl.bufcols;
-  const int cols = pl.pcol0 + pl.nsl * pl.Mp;
-  if (cols > 512) return pl;
-  pl.tmem_cols = pow2_cols(cols);
+  pl.tmem_cols = pow2_cols(pl.pcol0 + (bwd ? 1 : 2) * pl.pbufcols);
   const size_t fixed = 1024 /*alignment*/ + (size_t)2 * pl.Mp * 128 * pl.nkb + kStatFloats * 4 + 1024 /*barriers*/;
   const size_t avail = 227 * 1024;
-  if (fixed + 6 * (size_t)kSlotBytes > avail) return pl;
-  pl.nslots = (int)std::min<size_t>(12, (avail - fixed) / kSlotBytes);
-  pl.smem = fixed + (size_t)pl.nslots * kSlotBytes;
-  // chunks of the next sample fetched before the pooled phase: enough to cover the epilogue, bounded by the L2 budget
+  // rings: two or three tall bricks, the rest chunk stages (at least two)
+  pl.lbytes = (1 + pl.nfull) * kSlotBytes;
+  pl.nP = 2;
+  if (fixed + (size_t)pl.nP * kPBytes + 2 * (size_t)pl.lbytes > avail) return pl;
+  pl.nL = (int)std::min<size_t>(4, (avail - fixed - (size_t)pl.nP * kPBytes) / pl.lbytes);
+  if (fixed + (size_t)(pl.nP + 1) * kPBytes + (size_t)pl.nL * pl.lbytes <= avail) pl.nP = 3;
+  pl.smem = fixed + (size_t)pl.nP * kPBytes + (size_t)pl.nL * pl.lbytes;
+  pl.pf = ((g_debug >> 22) & 7) ? ((g_debug >> 22) & 7) - 1 : 3;  // dev knob: bits 22-24 = L2 prefetch distance + 1
+  // chunks of the next sample fetched before the first brick: enough to cover the epilogue, bounded by the L2 budget
   const size_t sample = (size_t)N * D * 2;
-  pl.lead = std::min(((g_debug >> 16) & 15) ? ((g_debug >> 16) & 15) - 1 : 2, pl.nchunks / 2);   // dev knob: bits 16-19 = lead + 1
+  pl.lead = std::min(((g_debug >> 16) & 15) ? ((g_debug >> 16) & 15) - 1 : 4, pl.nchunks / 2);   // dev knob: bits 16-19 = lead + 1
   if (pl.nbuf == 1) pl.lead = 0;                                  // a lead needs the second logit buffer
   while (pl.lead > 0 && sample * ctas * (pl.nchunks + pl.lead) / pl.nchunks > kL2Budget) --pl.lead;
   if (sample * ctas > kL2Budget) return pl;
@@ -590,21 +758,36 @@ int make_x_tmap(CUtensorMap* m, const void* x, int B, int N, int D, int rows) {
   return make_tmap_bf16(m, x, 3, dims, strides, box);
 }
 
+// tokens seen as (64 d, N, D / 64, B): a box of (64, rows, 2 * nb, 1) is nb bricks [rows tokens x 128 d], each as two
+// 128-byte-swizzled halves of 64 d
+int make_brick_tmap(CUtensorMap* m, const void* x, int B, int N, int D, int rows, int nb) {
+  const uint64_t dims[4] = {64, (uint64_t)N, (uint64_t)(D / 64), (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)D * 2, 128, (uint64_t)D * N * 2};
+  const uint32_t box[4] = {64, (uint32_t)rows, (uint32_t)(2 * nb), 1};
+  return make_tmap_bf16(m, x, 4, dims, strides, box);
+}
+
 template <bool kBwd>
 int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int N, int D, int M, const FPlan& pl, FParams p,
                  int grid, cudaStream_t s) {
-  CUtensorMap tm_x, tm_xt, tm_xb, tm_w;
+  CUtensorMap tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w;
   int rc;
-  if ((rc = make_x_tmap(&tm_x, x, B, N, D, 128))) return rc;
+  if ((rc = make_x_tmap(&tm_x, x, B, N, D, pl.nfull >= 2 ? 256 : 128))) return rc;
+  if ((rc = make_x_tmap(&tm_x1, x, B, N, D, 128))) return rc;
   if ((rc = make_x_tmap(&tm_xt, x, B, N, D, pl.tail_rows ? pl.tail_rows : 128))) return rc;
-  if ((rc = make_x_tmap(&tm_xb, x, B, N, D, 64))) return rc;
+  if ((rc = make_brick_tmap(&tm_b, x, B, N, D, 128, 1))) return rc;
+  if ((rc = make_brick_tmap(&tm_bl, x, B, N, D, pl.last_rows, 1))) return rc;
   if ((rc = make_w_tmap(&tm_w, w, D, J, w_batched ? B : 1, pl.Mp))) return rc;
   p.B = B; p.N = N; p.D = D; p.M = M; p.Mp = pl.Mp;
   p.ntiles = pl.ntiles; p.nfull = pl.nfull; p.tail_rows = pl.tail_rows;
-  p.nchunks = pl.nchunks; p.nkb = pl.nkb; p.nsl = pl.nsl; p.nslots = pl.nslots; p.lead = pl.lead; p.nbuf = pl.nbuf;
+  p.nchunks = pl.nchunks; p.nkb = pl.nkb; p.nsl = pl.nsl; p.nL = pl.nL; p.nP = pl.nP; p.lbytes = pl.lbytes; p.nkp = pl.nkp; p.pf = pl.pf;
+  p.lead = pl.lead; p.nbuf = pl.nbuf;
+  p.nslg = pl.nslg; p.G = pl.G; p.pbufcols = pl.pbufcols; p.lsplit = pl.lsplit; p.lcolw = pl.lcolw; p.kl = pl.kl;
+  p.last_rows = pl.last_rows;
+  p.trace = (g_debug & 2048) ? 1 : 0; p.nomma = (g_debug & 4096) ? 1 : 0; p.noepi = (g_debug & 8192) ? 1 : 0;
   p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff;
   if ((rc = set_smem(fused_kernel<kBwd>, pl.smem))) return rc;
-  fused_kernel<kBwd><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_xt, tm_xb, tm_w, p);
+  fused_kernel<kBwd><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
   EP_LAUNCH_CHECK();
   return 0;
 }
@@ -612,13 +795,21 @@ int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int 
 }  // namespace fused
 using namespace fused;
 
-bool fused_supported(int N, int D, int M) { return make_fplan(N, D, M, stream_sms()).ok; }
+int fused_trace_fetch(long long* host_out, int n) {
+  if (n > 128) n = 128;
+  EP_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * sizeof(long long)));
+  return 0;
+}
+
+bool fused_supported(int N, int D, int M) {
+  return make_fplan(N, D, M, stream_sms(), false).ok && make_fplan(N, D, M, stream_sms(), true).ok;
+}
 
 // qhl: (J, D) bf16 hi/lo rows of the scaled queries
 int fused_pool_fwd(const void* x, const void* qhl, int J, int B, int N, int D, int M, float* P, float* S, float* rowmax,
                    float* rowsum, int round_p, cudaStream_t s) {
   const int grid = std::min(B, stream_sms());
-  const FPlan pl = make_fplan(N, D, M, grid);
+  const FPlan pl = make_fplan(N, D, M, grid, false);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   FParams p{};
   p.S = S; p.rmax = rowmax; p.rsum = rowsum; p.out = P; p.round_out = round_p;
@@ -629,7 +820,7 @@ int fused_pool_fwd(const void* x, const void* qhl, int J, int B, int N, int D, i
 int fused_pool_bwd(const void* x, const void* dphl, int J, int B, int N, int D, int M, const float* S, const float* rowmax,
                    const float* rowsum, const float* delta, float* part, int* groups_out, cudaStream_t s) {
   const int grid = std::min(B, stream_sms());
-  const FPlan pl = make_fplan(N, D, M, grid);
+  const FPlan pl = make_fplan(N, D, M, grid, true);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   FParams p{};
   p.S = const_cast<float*>(S); p.rmax = const_cast<float*>(rowmax); p.rsum = const_cast<float*>(rowsum);

@@ -69,6 +69,9 @@ int ep_set_debug(int flags);
 int ep_timing_count(void);
 int ep_timing_get(int i, char* name, int name_len, float* microseconds);
 int ep_timing_reset(void);
+/* Developer aid: with ep_set_debug bit 11 (2048) the one-pass fused kernels stamp clock64 at their pipeline
+ * hand-offs (CTA 0, first 8 samples, 16 stamps each); this copies the first n (<= 128) stamps to the host. */
+int ep_debug_trace(long long* host_out, int n);
 /* Which family ep_fwd/ep_bwd would use for this shape under the current mode (0 = none: forced tcgen05
  * but unsupported). */
 int ep_kernel_family_for(int x_dtype, int B, int N, int D, int M);

@@ -65,7 +65,7 @@ def timings(B, N, D, M, K=1000, flags=0, reps=5):
     print(f"timings B{B} N{N} D{D} M{M} flags={flags}: " + ", ".join(f"{k} {sum(v)/len(v):.1f}" for k, v in agg.items()), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "trace"):
     worst = 0.0
     worst = max(worst, compare(64, 257, 1024, 32, oracle=True))
     worst = max(worst, compare(64, 197, 768, 8, oracle=True))
@@ -80,7 +80,50 @@ if __name__ == "__main__":
         for M in (32, 8):
             timings(1024, 257, 1024, M)
             timings(1024, 257, 1024, M, flags=1024)
-        for lead in (0, 1, 3, 4):
+        for lead in (0, 2, 3, 6):
             timings(1024, 257, 1024, 32, flags=(lead + 1) << 16)
         timings(1024, 256, 1152, 32)
         timings(1024, 256, 1152, 32, flags=1024)
+
+
+def trace(B, N, D, M, bwd=False, flags=0):
+    """Pipeline hand-off stamps of CTA 0 (ep_set_debug bit 11), printed in microseconds at 1.965 GHz."""
+    import ctypes
+    torch.manual_seed(0)
+    head = E.make_ep_head(D, M, 1000).to(DEV)
+    tr = E.EPHeadTrainer(head, B, N, lr=0.1, use_graph=False)
+    x = torch.randn(B, N, D, device=DEV).to(torch.bfloat16)
+    y = torch.randint(0, 1000, (B,), device=DEV)
+    tr.train_step(x, y)
+    torch.cuda.synchronize()
+    lib.ep_set_debug(2048 | flags)
+    if bwd:
+        tr._cx, tr._ct = x, y
+        tr._part2()
+    else:
+        tr._cx, tr._ct = x, y
+        tr._forward(True)
+    torch.cuda.synchronize()
+    lib.ep_set_debug(0)
+    buf = (ctypes.c_longlong * 128)()
+    lib.ep_debug_trace(ctypes.cast(buf, ctypes.c_void_p), 128)
+    t = [buf[i] for i in range(128)]
+    t0 = min(v for v in t[:112] if v > 0)
+    names = {0: "P:wait_blocks", 1: "P:start", 3: "P:issued", 2: "L:issued", 8: "epi:begin", 9: "epi:logits_ready",
+             10: "epi:P_prev_done", 12: "epi:blocks_written", 13: "epi:drains_done"}
+    print(f"trace {'bwd' if bwd else 'fwd'} B{B} N{N} D{D} M{M}")
+    for i in range(2, 5):
+        row = sorted((t[i * 16 + k], names[k]) for k in names if t[i * 16 + k] > 0)
+        print(f"  sample {i}: " + "  ".join(f"{nm}@{(v - t0) / 1965.0:.1f}" for v, nm in row))
+    print(f"  L producer: ring-full wait {t[120] / 1965.0:.1f} us of {t[121] / 1965.0:.1f};  P producer: {t[125] / 1965.0:.1f} of {t[126] / 1965.0:.1f};  "
+          f"L warp: load wait {t[122] / 1965.0:.1f} us, order wait {t[123] / 1965.0:.1f} us of {t[124] / 1965.0:.1f};  "
+          f"P warp: load wait {t[117] / 1965.0:.1f} us, block wait {t[118] / 1965.0:.1f} us of {t[119] / 1965.0:.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "trace":
+    trace(1024, 257, 1024, 32)
+    trace(1024, 257, 1024, 32, flags=4096)
+    trace(1024, 257, 1024, 32, flags=8192)
+    trace(1024, 257, 1024, 32, flags=8192 | 4096)
+    trace(1024, 257, 1024, 32, bwd=True)
+    trace(1024, 257, 1024, 8)
