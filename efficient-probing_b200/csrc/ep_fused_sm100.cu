@@ -56,7 +56,7 @@ constexpr int kSlotBytes = 16384;      // ring slot: [128 tokens x 64 d] chunk t
 constexpr int kEW = 16;                // epilogue warps
 constexpr int kSub = kEW / 4;          // ... per TMEM lane quadrant
 constexpr int kThreadsF = 32 * (4 + kEW);
-constexpr int kStatFloats = 2 * kEW * 64 + 128;   // per-warp partial max / sum of up to 64 queries + [2][64] row sums
+__host__ __device__ constexpr int stat_floats(int Mp) { return 2 * kEW * Mp + 128; }   // per-warp partial max / sum [kEW][Mp] + [2][64] row sums
 constexpr int kCache = 2;              // logit units a warp keeps in registers between the two softmax passes
 
 // developer trace (ep_set_debug bit 11): clock64 stamps of CTA 0's MMA warp and epilogue warp 4, 16 stamps x 8 samples
@@ -67,7 +67,7 @@ struct FParams {
   int B, N, D, M, Mp;                  // Mp = M rounded up to 16: UMMA N, accumulator columns per tile / slice
   int ntiles, nfull, tail_rows;        // token tiles of 128; nfull of them loaded as full boxes; tail_rows > 0: the last
                                        // tile is a short box sharing its slot with the query chunk
-  int nchunks, nkb, nsl, nL, nP, lbytes, lead, nbuf, bufcols, pcol0, tmem_cols, w_batched, qoff;   // nL/nP ring stages
+  int nchunks, nkb, nsl, nL, nP, lbytes, lead, nbuf, bufcols, pcol0, tmem_cols, w_batched, qoff, toff;   // nL/nP ring stages; chunk stage = [tail tile @0][query chunk @qoff][token tiles @toff]
   int nkp, pf;                         // tall bricks per slice (= ceil(nkb / 2)); L2 prefetch distance in chunks
   int nslg, G, pbufcols;               // pooled phase: G groups of <= nslg slices, accumulator buffers of pbufcols columns
   int lsplit;                          // logit phase: 1 = hi/lo query rows as two K-steps into one column (N = Mp),
@@ -141,7 +141,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   const uint32_t blk_base = pring + (uint32_t)p.nP * kPBytes;
   const uint32_t blk_bytes = 2u * half_bytes * (uint32_t)p.nkb;
   const uint32_t stat_base = blk_base + blk_bytes;
-  const uint32_t bar_base = stat_base + kStatFloats * 4u;
+  const uint32_t bar_base = stat_base + (uint32_t)stat_floats(p.Mp) * 4u;
   auto lfull_bar = [&](int s) { return bar_base + 8u * s; };              // L ring stage s loaded / consumed
   auto lempty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
   auto pfull_bar = [&](int s) { return bar_base + 64u + 8u * s; };         // P ring
@@ -189,10 +189,11 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   const int tile_rows = p.nfull * 128;
 
   if (warp == 0) {
-    // ---- L producer: chunk after chunk, sample after sample, into the L ring; stage = [slot 0: short tail tile at 0,
-    // query chunk at qoff][nfull x 16 KB token tiles]
+    // ---- L producer: chunk after chunk, sample after sample, into the L ring; stage = [short tail tile][query chunk at
+    // qoff][nfull x 16 KB token tiles at toff]
     if (lane == 0 && nmine > 0) {
       const uint64_t pol_last = policy_evict_last();
+      const uint64_t pol_w = p.w_batched ? policy_evict_first() : pol_last;   // per-sample dP rows are read once
       const uint32_t tx = w_bytes + (mixed_tail ? (uint32_t)p.tail_rows * 128u : 0u) + (uint32_t)p.nfull * kSlotBytes;
       int s = 0;
       uint32_t ph = 0;
@@ -207,9 +208,9 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const uint32_t bar = lfull_bar(s), dst = ring + (uint32_t)(s * p.lbytes);
           mbar_arrive_expect_tx(bar, tx);
           for (int r = 0; r < tile_rows; r += 256)                 // two tiles per instruction, a last odd one alone
-            tma_load_3d_hint(dst + kSlotBytes + (uint32_t)r * 128u, tile_rows - r >= 256 ? &tm_x : &tm_x1, bar, c * 64, r, b, pol_last);
-          tma_load_4d_hint(dst + (uint32_t)p.qoff, &tm_w, bar, c * 64, 0, 0, zb, pol_last);
-          tma_load_4d_hint(dst + (uint32_t)p.qoff + half_bytes, &tm_w, bar, c * 64, 1, 0, zb, pol_last);
+            tma_load_3d_hint(dst + (uint32_t)p.toff + (uint32_t)r * 128u, tile_rows - r >= 256 ? &tm_x : &tm_x1, bar, c * 64, r, b, pol_last);
+          tma_load_4d_hint(dst + (uint32_t)p.qoff, &tm_w, bar, c * 64, 0, 0, zb, pol_w);
+          tma_load_4d_hint(dst + (uint32_t)p.qoff + half_bytes, &tm_w, bar, c * 64, 1, 0, zb, pol_w);
           if (mixed_tail) tma_load_3d_hint(dst, &tm_xt, bar, c * 64, tile_rows, b, pol_last);
           if (p.pf > 0) {                                          // the chunk pf ahead (maybe of the next sample) -> L2
             int cp = c + p.pf, bp = b;
@@ -271,7 +272,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             tc_fence_after();
           }
           if (j > 0) {
-            const int need = c < p.lead ? (j - 1) * nst : (j - 1) * nst + (c - p.lead + 1) * nst / (p.nchunks - p.lead);
+            const int need = (j - 1) * nst + (c > p.lead ? (c - p.lead) * nst / p.nchunks : 0);
             while (*p_issued < need) {}
           }
           if (p.trace) t_gate += clock64() - tg;
@@ -282,8 +283,9 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const uint64_t bd = dK + (uint64_t)((st0 + (uint32_t)p.qoff) >> 4);
           if (leader && !p.nomma) {
             for (int t = 0; t < p.ntiles; ++t) {
-              // full tiles follow slot 0, the short tail tile sits at its start
-              const uint64_t ad = dK + (uint64_t)((t < p.nfull ? st0 + (uint32_t)(1 + t) * kSlotBytes : st0) >> 4);
+              // full tiles at toff, the short tail tile at the start of the stage (the MMA reads 128 rows there: the
+              // rows past the tail are the query chunk / first tile and only reach accumulator rows n >= N)
+              const uint64_t ad = dK + (uint64_t)((t < p.nfull ? st0 + (uint32_t)p.toff + (uint32_t)t * kSlotBytes : st0) >> 4);
               const uint32_t d = acc + (uint32_t)(t * p.lcolw);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -370,9 +372,11 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   } else if (warp >= 4) {
     const int ew = warp - 4, wq = ew & 3, es = ew >> 2;            // quadrant, sub-warp within the quadrant
     const int upt = p.Mp >> 4;                                     // 16-query units per tile / slice
-    float* pmax = reinterpret_cast<float*>(gen + (stat_base - ring));   // [kEW][64]
-    float* psum = pmax + kEW * 64;                                      // [kEW][64]
-    float* tot = psum + kEW * 64;                                       // [2][64] softmax row sums, by sample parity
+    const int SW = p.Mp;                                                // table row stride
+    float* pmax = reinterpret_cast<float*>(gen + (stat_base - ring));   // [kEW][Mp]
+    float* psum = pmax + kEW * SW;                                      // [kEW][Mp]
+    float* tot = psum + kEW * SW;                                       // [2][64] softmax row sums, by sample parity
+    const bool has_lo = lane < SW, has_hi = 32 + lane < SW;             // this lane's table columns l and 32 + l exist
     uint8_t* blk_gen = gen + (blk_base - ring);
     const int ridx = reduce16_index(lane);
     const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
@@ -405,11 +409,12 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             if (p.round_out) {                                     // P as bf16 hi/lo rows (b, m, {hi, lo}, d)
               const __nv_bfloat16 hi = __float2bfloat16_rn(v);
               const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-              __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
-              pr[0] = hi;
-              pr[p.D] = lo;
+              // streaming stores (evict-first in L2): the outputs must not displace the tokens waiting for their second fetch
+              unsigned short* pr = reinterpret_cast<unsigned short*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
+              __stcs(pr, __bfloat16_as_ushort(hi));
+              __stcs(pr + p.D, __bfloat16_as_ushort(lo));
             } else {
-              p.out[((size_t)b * p.M + m) * p.D + d] = v;
+              __stcs(p.out + ((size_t)b * p.M + m) * p.D + d, v);
             }
           }
         }
@@ -467,8 +472,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       if (!kBwd && !p.noepi) {
         // ---- pass 1: per-query maximum over the tokens (per-warp partial rows, combined in a fixed order); the
         // first kCache units of a warp stay in registers for pass 2
-        pmax[ew * 64 + lane] = -INFINITY;
-        pmax[ew * 64 + 32 + lane] = -INFINITY;
+        if (has_lo) pmax[ew * SW + lane] = -INFINITY;
+        if (has_hi) pmax[ew * SW + 32 + lane] = -INFINITY;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < kCache; ++k) {
@@ -481,7 +486,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? cache[k][q] : -INFINITY;
             const float red = reduce16<true>(v, lane);
             if ((lane & 1) == 0) {
-              float* slot = pmax + ew * 64 + j0 + ridx;
+              float* slot = pmax + ew * SW + j0 + ridx;
               *slot = fmaxf(*slot, red);
             }
             __syncwarp();
@@ -496,18 +501,22 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? v[q] : -INFINITY;
           const float red = reduce16<true>(v, lane);
           if ((lane & 1) == 0) {
-            float* slot = pmax + ew * 64 + j0 + ridx;
+            float* slot = pmax + ew * SW + j0 + ridx;
             *slot = fmaxf(*slot, red);
           }
           __syncwarp();
         }
       }
-      if (i > 0) {                                                 // every pooled MMA of sample i - 1 complete: blocks reusable
-        const int gl = kBwd ? 2 * (i - 1) : i * p.G - 1;           // its last group
-        mbar_wait(pdone_bar(gl & 1), ((uint32_t)(gl >> 1)) & 1u);
-        tc_fence_after();
-        if (warp == 4) EP_TRACE(i, 10);                            // epilogue: pooled MMAs of sample i - 1 complete
-      }
+      // the operand blocks may be rewritten once every pooled MMA of sample i - 1 has completed
+      auto wait_blocks_free = [&]() {
+        if (i > 0) {
+          const int gl = kBwd ? 2 * (i - 1) : i * p.G - 1;         // its last group
+          mbar_wait(pdone_bar(gl & 1), ((uint32_t)(gl >> 1)) & 1u);
+          tc_fence_after();
+          if (warp == 4) EP_TRACE(i, 10);                          // epilogue: pooled MMAs of sample i - 1 complete
+        }
+      };
+      if (kBwd || p.noepi) wait_blocks_free();
       if (p.noepi) {
         tc_fence_before();
         __syncwarp();
@@ -523,45 +532,62 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         float mx_lo = -INFINITY, mx_hi = -INFINITY;                // lane l: queries l and 32 + l
 #pragma unroll
         for (int w = 0; w < kEW; ++w) {
-          mx_lo = fmaxf(mx_lo, pmax[w * 64 + lane]);
-          mx_hi = fmaxf(mx_hi, pmax[w * 64 + 32 + lane]);
+          if (has_lo) mx_lo = fmaxf(mx_lo, pmax[w * SW + lane]);
+          if (has_hi) mx_hi = fmaxf(mx_hi, pmax[w * SW + 32 + lane]);
         }
-        psum[ew * 64 + lane] = 0.f;
-        psum[ew * 64 + 32 + lane] = 0.f;
+        if (has_lo) psum[ew * SW + lane] = 0.f;
+        if (has_hi) psum[ew * SW + 32 + lane] = 0.f;
         __syncwarp();
-        // ---- pass 2: exp, row sums, saved logits, operand blocks
-        auto emit = [&](int t, int j0, const float (&v)[16]) {
+        // ---- pass 2a (cached units; overlaps the tail of the previous sample's pooled phase): exp, row sums, saved
+        // logits -- the probabilities replace the logits in the register cache
+        auto emit = [&](int t, int j0, float (&v)[16], bool to_blocks) {
           const int n = t * 128 + wq * 32 + lane;
           const bool valid = n < p.N;
           const int kb = n >> 6, tt = n & 63;
-          uint8_t* blk = kb < p.nkb ? blk_gen + (size_t)kb * 2u * half_bytes : nullptr;
+          uint8_t* blk = (to_blocks && kb < p.nkb) ? blk_gen + (size_t)kb * 2u * half_bytes : nullptr;
           float* srow = p.S + ((size_t)b * p.M + j0) * p.N + n;
-          float e[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const int m = j0 + q;                                  // warp-uniform
             const float mx = __shfl_sync(0xffffffffu, m < 32 ? mx_lo : mx_hi, m & 31);
             const bool on = valid && m < p.M;
-            e[q] = on ? __expf(v[q] - mx) : 0.f;
-            if (on) srow[(size_t)q * p.N] = v[q];
-            if (blk && m < p.M) store_hilo(blk, m, tt, e[q]);
+            if (on) __stcs(srow + (size_t)q * p.N, v[q]);
+            v[q] = on ? __expf(v[q] - mx) : 0.f;
+            if (blk && m < p.M) store_hilo(blk, m, tt, v[q]);
           }
-          const float red = reduce16<false>(e, lane);
-          if ((lane & 1) == 0) psum[ew * 64 + j0 + ridx] += red;
+          const float red = reduce16<false>(v, lane);
+          if ((lane & 1) == 0) psum[ew * SW + j0 + ridx] += red;
           __syncwarp();
         };
 #pragma unroll
         for (int k = 0; k < kCache; ++k) {
           const int u = es + kSub * k;
           const int t = u / upt, j0 = (u - t * upt) << 4;
-          if (u < nunits && t * 128 + wq * 32 < p.N) emit(t, j0, cache[k]);
+          if (u < nunits && t * 128 + wq * 32 < p.N) emit(t, j0, cache[k], false);
+        }
+        // ---- pass 2b: the operand blocks, once the previous sample's pooled MMAs have stopped reading them
+        wait_blocks_free();
+#pragma unroll
+        for (int k = 0; k < kCache; ++k) {
+          const int u = es + kSub * k;
+          const int t = u / upt, j0 = (u - t * upt) << 4;
+          if (u < nunits && t * 128 + wq * 32 < p.N) {
+            const int n = t * 128 + wq * 32 + lane;
+            const int kb = n >> 6, tt = n & 63;
+            if (kb < p.nkb) {
+              uint8_t* blk = blk_gen + (size_t)kb * 2u * half_bytes;
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (j0 + q < p.M) store_hilo(blk, j0 + q, tt, cache[k][q]);
+            }
+          }
         }
         for (int u = es + kSub * kCache; u < nunits; u += kSub) {
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
           load_unit(acc, t, j0, v);
-          emit(t, j0, v);
+          emit(t, j0, v, true);
         }
         fence_proxy_async();                                       // generic-proxy block writes -> visible to the MMAs
         tc_fence_before();
@@ -577,7 +603,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const int m = 32 * h + lane;
             float su = 0.f;
 #pragma unroll
-            for (int w = 0; w < kEW; ++w) su += psum[w * 64 + m];
+            if (m < SW)
+              for (int w = 0; w < kEW; ++w) su += psum[w * SW + m];
             tot[(i & 1) * 64 + m] = su;
             if (m < p.M) {
               p.rmax[(size_t)b * p.M + m] = h ? mx_hi : mx_lo;
@@ -602,7 +629,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 #pragma unroll
           for (int q = 0; q < 16; ++q) {                           // issued before the TMEM wait: independent loads
             const int m = min(j0 + q, p.M - 1);
-            sv[q] = valid ? __ldg(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
+            sv[q] = valid ? __ldcs(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
           }
           float v[16];
           load_unit(acc, t, j0, v);
@@ -664,7 +691,7 @@ int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 
 struct FPlan {
   bool ok = false;
-  int Mp, ntiles, nfull, tail_rows, nchunks, nkb, nsl, nL, nP, lbytes, nkp, pf, lead, nbuf, bufcols, pcol0, tmem_cols, qoff, nslg, G, pbufcols;
+  int Mp, ntiles, nfull, tail_rows, nchunks, nkb, nsl, nL, nP, lbytes, nkp, pf, lead, nbuf, bufcols, pcol0, tmem_cols, qoff, toff, nslg, G, pbufcols;
   int lsplit, lcolw, kl, last_rows;
   size_t smem;
 };
@@ -679,10 +706,11 @@ FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   pl.ntiles = (N + 127) / 128;
   const int rem = N - (pl.ntiles - 1) * 128;                      // rows of the last tile
   const int w_bytes = 2 * pl.Mp * 128;
-  // the short last tile rides in the query chunk's slot when both fit in 16 KB
-  pl.tail_rows = (rem < 128 && (rem + 7) / 8 * 8 * 128 + w_bytes <= kSlotBytes) ? (rem + 7) / 8 * 8 : 0;
+  // a last tile of at most 64 tokens is loaded as a short box in front of the query chunk
+  pl.tail_rows = rem <= 64 ? (rem + 7) / 8 * 8 : 0;
   pl.nfull = pl.tail_rows ? pl.ntiles - 1 : pl.ntiles;
-  pl.qoff = kSlotBytes - w_bytes;
+  pl.qoff = pl.tail_rows * 128;
+  pl.toff = pl.qoff + w_bytes;
   pl.nchunks = D / 64;
   pl.nkb = (N + 63) / 64;
   pl.nsl = D / 128;
@@ -717,21 +745,22 @@ FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   pl.bufcols = pl.ntiles * pl.lcolw;
   pl.pcol0 = pl.nbuf * pl.bufcols;
   pl.tmem_cols = pow2_cols(pl.pcol0 + (bwd ? 1 : 2) * pl.pbufcols);
-  const size_t fixed = 1024 /*alignment*/ + (size_t)2 * pl.Mp * 128 * pl.nkb + kStatFloats * 4 + 1024 /*barriers*/;
+  const size_t fixed = 1024 /*alignment*/ + (size_t)2 * pl.Mp * 128 * pl.nkb + (size_t)stat_floats(pl.Mp) * 4 + 1024 /*barriers*/;
   const size_t avail = 227 * 1024;
   // rings: two or three tall bricks, the rest chunk stages (at least two)
-  pl.lbytes = (1 + pl.nfull) * kSlotBytes;
+  pl.lbytes = pl.toff + pl.nfull * kSlotBytes;
   pl.nP = 2;
   if (fixed + (size_t)pl.nP * kPBytes + 2 * (size_t)pl.lbytes > avail) return pl;
   pl.nL = (int)std::min<size_t>(4, (avail - fixed - (size_t)pl.nP * kPBytes) / pl.lbytes);
   if (fixed + (size_t)(pl.nP + 1) * kPBytes + (size_t)pl.nL * pl.lbytes <= avail) pl.nP = 3;
   pl.smem = fixed + (size_t)pl.nP * kPBytes + (size_t)pl.nL * pl.lbytes;
-  pl.pf = ((g_debug >> 22) & 7) ? ((g_debug >> 22) & 7) - 1 : 3;  // dev knob: bits 22-24 = L2 prefetch distance + 1
+  pl.pf = ((g_debug >> 22) & 7) ? ((g_debug >> 22) & 7) - 1 : 0;  // dev knob: bits 22-24 = L2 prefetch distance + 1
   // chunks of the next sample fetched before the first brick: enough to cover the epilogue, bounded by the L2 budget
   const size_t sample = (size_t)N * D * 2;
   pl.lead = std::min(((g_debug >> 16) & 15) ? ((g_debug >> 16) & 15) - 1 : 4, pl.nchunks / 2);   // dev knob: bits 16-19 = lead + 1
   if (pl.nbuf == 1) pl.lead = 0;                                  // a lead needs the second logit buffer
-  while (pl.lead > 0 && sample * ctas * (pl.nchunks + pl.lead) / pl.nchunks > kL2Budget) --pl.lead;
+  const size_t budget = kL2Budget + ((size_t)((g_debug >> 25) & 7) * 10 << 20);   // dev knob: bits 25-27 = +10 MB each
+  while (pl.lead > 0 && sample * ctas * (pl.nchunks + pl.lead) / pl.nchunks > budget) --pl.lead;
   if (sample * ctas > kL2Budget) return pl;
   pl.ok = true;
   return pl;
@@ -785,7 +814,7 @@ int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int 
   p.nslg = pl.nslg; p.G = pl.G; p.pbufcols = pl.pbufcols; p.lsplit = pl.lsplit; p.lcolw = pl.lcolw; p.kl = pl.kl;
   p.last_rows = pl.last_rows;
   p.trace = (g_debug & 2048) ? 1 : 0; p.nomma = (g_debug & 4096) ? 1 : 0; p.noepi = (g_debug & 8192) ? 1 : 0;
-  p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff;
+  p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff; p.toff = pl.toff;
   if ((rc = set_smem(fused_kernel<kBwd>, pl.smem))) return rc;
   fused_kernel<kBwd><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
   EP_LAUNCH_CHECK();

@@ -65,7 +65,7 @@ def timings(B, N, D, M, K=1000, flags=0, reps=5):
     print(f"timings B{B} N{N} D{D} M{M} flags={flags}: " + ", ".join(f"{k} {sum(v)/len(v):.1f}" for k, v in agg.items()), flush=True)
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "trace"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("trace", "sweep")):
     worst = 0.0
     worst = max(worst, compare(64, 257, 1024, 32, oracle=True))
     worst = max(worst, compare(64, 197, 768, 8, oracle=True))
@@ -119,6 +119,12 @@ def trace(B, N, D, M, bwd=False, flags=0):
           f"L warp: load wait {t[122] / 1965.0:.1f} us, order wait {t[123] / 1965.0:.1f} us of {t[124] / 1965.0:.1f};  "
           f"P warp: load wait {t[117] / 1965.0:.1f} us, block wait {t[118] / 1965.0:.1f} us of {t[119] / 1965.0:.1f}")
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweep":
+    for lead in (2, 4, 6, 8):
+        for pf in (0, 3, 6):
+            print(f"lead {lead} pf {pf}", end=": ")
+            timings(1024, 257, 1024, 32, flags=((lead + 1) << 16) | ((pf + 1) << 22) | (4 << 25))
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "trace":
     trace(1024, 257, 1024, 32)
