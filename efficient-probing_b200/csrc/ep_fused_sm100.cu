@@ -38,6 +38,19 @@
 // `lead` chunks) and the epilogue has released the logit buffer.  The L producer also prefetches into L2 a few chunks
 // ahead (cp.async.bulk.prefetch.tensor), so that the two chunk stages shared memory has room for cover L2 latency.
 //
+// What was measured (profiles/r02_*): with 148 CTAs the live tokens (148 x (one sample + lead) = 80-100 MB at c2) do
+// NOT survive in L2 between their two fetches -- dram__bytes_read is 1.0 GB per pass at c2, twice the tokens; it is
+// 0.55 GB with 74 CTAs.  About half of the 126 MB is usable for this pattern, so at c2 / c3 the second fetch is an
+// HBM read again and the kernel runs at the speed of the two kernels it replaces (it still saves their operand
+// blocks and launches).  Shapes whose 148 samples fit (N x D x 2 B <= ~390 KB) get the single HBM read.
+//
+// Pair mode (developer knob, ep_set_debug bit 29).  CTAs 2k and 2k+1 share sample k, 74 + k, ...: each takes half of
+// the d-slices in BOTH phases (half the chunks, half the bricks), the partial logits are exchanged through a global
+// scratch buffer that lives in L2 (written, fenced, flag released; the partner polls the flag with an acquire load --
+// all 148 CTAs are co-resident, one per SM), and both CTAs run the same softmax on the sum, so each has every
+// probability for its own slices.  Live tokens: 74 samples instead of 148 -- DRAM reads fall to 0.73 GB at c2 -- but
+// the softmax epilogue is now done twice per sample and the pass takes 340 us against 245 us: not the default.
+//
 // Warp roles (one CTA per SM): warp 0 L producer, warp 1 L MMA issuer, warp 2 TMEM allocator + P MMA issuer, warp 3 P
 // producer, warps 4.. epilogue (kEW warps, kEW / 4 per TMEM lane quadrant).
 #include <cuda.h>
@@ -79,6 +92,10 @@ struct FParams {
   const float* delta;                  // bwd: (B, M)
   float* out;                          // fwd: P as bf16 hi/lo rows (B, M, 2, D) or fp32 (B, M, D);  bwd: partial dq [grid][M][D]
   int round_out;
+  int pair;                            // 1: two CTAs (2k, 2k+1) share a sample, each takes half of D (see header)
+  int nslA;                            // pair mode: d-slices of CTA 2k (the rest belong to CTA 2k+1)
+  float* xchg;                         // pair mode: partial-logit exchange [cta][2][ntiles][Mp][128] fp32
+  int* flags;                          // pair mode: per CTA, samples whose partial logits are published (zeroed before launch)
   int trace;
   int noepi;                           // developer: epilogue warps only run the barrier protocol
   int nomma;                           // developer: skip the MMA instructions (timing experiments; results are garbage)
@@ -180,8 +197,14 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // this CTA's samples, d-chunks [c_lo, c_lo + nch) and d-slices [sl_lo, sl_lo + nslh)
+  const int cta = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int half = p.pair ? (int)(blockIdx.x & 1) : 0;
+  const int sl_lo = half ? p.nslA : 0, nslh = p.pair ? (half ? p.nsl - p.nslA : p.nslA) : p.nsl;
+  const int c_lo = 2 * sl_lo, nch = 2 * nslh;
+  const int G = (nslh + p.nslg - 1) / p.nslg;                     // pooled groups of this CTA (fwd; bwd plans one group)
   int nmine = 0;
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) ++nmine;
+  for (int b = cta; b < p.B; b += ncta) ++nmine;
   const uint32_t w_bytes = 2u * half_bytes;                       // query / dP chunk: hi rows then lo rows
   const bool mixed_tail = p.tail_rows > 0;                        // the short last tile shares the query chunk's slot
 
@@ -199,9 +222,9 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       uint32_t ph = 0;
       long long t_wait = 0, t_begin = clock64();
       for (int i = 0; i < nmine; ++i) {
-        const int b = blockIdx.x + i * gridDim.x;
+        const int b = cta + i * ncta;
         const int zb = p.w_batched ? b : 0;
-        for (int c = 0; c < p.nchunks; ++c) {
+        for (int c = c_lo; c < c_lo + nch; ++c) {
           const long long t0 = p.trace ? clock64() : 0;
           mbar_wait(lempty_bar(s), ph ^ 1u);
           if (p.trace) t_wait += clock64() - t0;
@@ -214,7 +237,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           if (mixed_tail) tma_load_3d_hint(dst, &tm_xt, bar, c * 64, tile_rows, b, pol_last);
           if (p.pf > 0) {                                          // the chunk pf ahead (maybe of the next sample) -> L2
             int cp = c + p.pf, bp = b;
-            if (cp >= p.nchunks) { cp -= p.nchunks; bp += gridDim.x; }
+            if (cp >= c_lo + nch) { cp -= nch; bp += ncta; }
             if (bp < p.B) {
               for (int r = 0; r < tile_rows; r += 256) tma_prefetch_3d(tile_rows - r >= 256 ? &tm_x : &tm_x1, cp * 64, r, bp, pol_last);
               if (mixed_tail) tma_prefetch_3d(&tm_xt, cp * 64, tile_rows, bp, pol_last);
@@ -235,8 +258,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       uint32_t ph = 0;
       long long t_wait = 0, t_begin = clock64();
       for (int i = 0; i < nmine; ++i) {
-        const int b = blockIdx.x + i * gridDim.x;
-        for (int sl = 0; sl < p.nsl; ++sl)
+        const int b = cta + i * ncta;
+        for (int sl = sl_lo; sl < sl_lo + nslh; ++sl)
           for (int kp = 0; kp < p.nkp; ++kp) {
             const long long t0 = p.trace ? clock64() : 0;
             mbar_wait(pempty_bar(s), ph ^ 1u);
@@ -257,13 +280,13 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const uint32_t idesc_L = idesc_bf16(128, p.lsplit ? p.Mp : 2 * p.Mp, 0, 0);
       const uint64_t dK = smem_desc_sw128(0, 16, 1024);           // + (address >> 4)
       const uint64_t lo_off = (uint64_t)(half_bytes >> 4);
-      const int nst = p.nsl * p.nkp;                               // tall bricks per sample
+      const int nst = nslh * p.nkp;                                // tall bricks per sample (of this CTA)
       int ls = 0;
       uint32_t lph = 0;
       long long t_wait = 0, t_gate = 0, t_begin = clock64();
       for (int j = 0; j < nmine; ++j) {
         const uint32_t acc = tmem_base + (uint32_t)((j % p.nbuf) * p.bufcols);
-        for (int c = 0; c < p.nchunks; ++c) {
+        for (int c = 0; c < nch; ++c) {
           // order against the other stream: the logit buffer is free (its previous sample's epilogue has read it), and
           // chunk c runs at most `lead` chunks ahead of the matching share of the previous sample's bricks
           const long long tg = p.trace ? clock64() : 0;
@@ -272,7 +295,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             tc_fence_after();
           }
           if (j > 0) {
-            const int need = (j - 1) * nst + (c > p.lead ? (c - p.lead) * nst / p.nchunks : 0);
+            const int need = (j - 1) * nst + (c > p.lead ? (c - p.lead) * nst / nch : 0);
             while (*p_issued < need) {}
           }
           if (p.trace) t_gate += clock64() - tg;
@@ -326,13 +349,13 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         tc_fence_after();
         if (p.trace) t_gate += clock64() - tg;
         EP_TRACE(i, 1);                                            // P warp: pooled phase starts
-        for (int g = 0; g < p.G; ++g) {
-          const int gg = kBwd ? 2 * i : i * p.G + g;               // bwd: one group per sample, always buffer 0
+        for (int g = 0; g < (kBwd ? 1 : G); ++g) {
+          const int gg = kBwd ? 2 * i : i * G + g;                 // bwd: one group per sample, always buffer 0
           if (!kBwd) {                                             // this buffer's previous group has been drained
             mbar_wait(pfree_bar(gg & 1), (((uint32_t)(gg >> 1)) & 1u) ^ 1u);
             tc_fence_after();
           }
-          const int gs = min(p.nslg, p.nsl - g * p.nslg);
+          const int gs = kBwd ? nslh : min(p.nslg, nslh - g * p.nslg);
           for (int slg = 0; slg < gs; ++slg) {
             const uint32_t pacc = tmem_base + (uint32_t)p.pcol0 + (kBwd ? 0u : (uint32_t)((gg & 1) * p.pbufcols)) + (uint32_t)slg * pcolw;
             for (int kp = 0; kp < p.nkp; ++kp) {
@@ -384,18 +407,18 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 
     // fwd: group g of sample ordinal i (accumulator buffer gg & 1) -> normalised P rows in global memory
     auto drain_group = [&](int b, int i, int g) {
-      const int gg = i * p.G + g;
+      const int gg = i * G + g;
       mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_base + (uint32_t)(p.pcol0 + (gg & 1) * p.pbufcols);
-      const int gs = min(p.nslg, p.nsl - g * p.nslg);
+      const int gs = min(p.nslg, nslh - g * p.nslg);
       float invl[2] = {1.f, 1.f};                                  // lane l keeps 1/rowsum of queries l and 32 + l
 #pragma unroll
       for (int h = 0; h < 2; ++h)
         if (h * 32 + lane < p.M) invl[h] = 1.f / tot[(i & 1) * 64 + h * 32 + lane];
       for (int u = es; u < gs * upt; u += kSub) {
         const int slg = u / upt, j0 = (u - slg * upt) << 4;
-        const int d = (g * p.nslg + slg) * 128 + wq * 32 + lane;
+        const int d = (sl_lo + g * p.nslg + slg) * 128 + wq * 32 + lane;
         uint32_t rh[16], rl[16];
         tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + j0), rh);
         tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + p.Mp + j0), rl);
@@ -446,7 +469,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     };
 
     for (int i = 0; i < nmine; ++i) {
-      const int b = blockIdx.x + i * gridDim.x;
+      const int b = cta + i * ncta;
       const int buf = i % p.nbuf;
       if (warp == 4) EP_TRACE(i, 8);                               // epilogue: sample i begins
       // bwd: lane l keeps the row statistics of queries l and 32 + l of this sample
@@ -468,6 +491,40 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       if (warp == 4) EP_TRACE(i, 9);                               // epilogue: logits complete
       const uint32_t acc = tmem_base + lane_base + (uint32_t)(buf * p.bufcols);
       float cache[kCache][16];
+      // pair mode: publish this CTA's partial logits (its half of D), then wait for the partner's; from here on
+      // fetch_unit() returns the sum.  Scratch slot i & 1: the partner read slot i & 1 of sample i - 2 before it
+      // published sample i - 1, which this CTA has already consumed.
+      const float* peer = nullptr;
+      if (p.pair && !p.noepi) {
+        const size_t slot_floats = (size_t)p.ntiles * p.Mp * 128;
+        float* mine = p.xchg + ((size_t)blockIdx.x * 2 + (i & 1)) * slot_floats;
+        peer = p.xchg + ((size_t)(blockIdx.x ^ 1) * 2 + (i & 1)) * slot_floats;
+        for (int u = es, k = 0; u < nunits; u += kSub, ++k) {
+          const int t = u / upt, j0 = (u - t * upt) << 4;
+          if (t * 128 + wq * 32 >= p.N) continue;
+          float v[16];
+          load_unit(acc, t, j0, v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) __stcg(mine + ((size_t)t * p.Mp + j0 + q) * 128 + wq * 32 + lane, v[q]);
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
+        if (ew == 0 && lane == 0) {
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(i + 1) : "memory");
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.flags + (blockIdx.x ^ 1)) : "memory");
+          } while (seen < i + 1);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
+      }
+      auto fetch_unit = [&](int t, int j0, float (&v)[16]) {
+        load_unit(acc, t, j0, v);
+        if (peer) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] += __ldcg(peer + ((size_t)t * p.Mp + j0 + q) * 128 + wq * 32 + lane);
+        }
+      };
 
       if (!kBwd && !p.noepi) {
         // ---- pass 1: per-query maximum over the tokens (per-warp partial rows, combined in a fixed order); the
@@ -480,7 +537,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const int u = es + kSub * k;
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (u < nunits && t * 128 + wq * 32 < p.N) {             // (warp-uniform) some lane of this warp holds a token
-            load_unit(acc, t, j0, cache[k]);
+            fetch_unit(t, j0, cache[k]);
             float v[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? cache[k][q] : -INFINITY;
@@ -496,7 +553,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
-          load_unit(acc, t, j0, v);
+          fetch_unit(t, j0, v);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? v[q] : -INFINITY;
           const float red = reduce16<true>(v, lane);
@@ -510,7 +567,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       // the operand blocks may be rewritten once every pooled MMA of sample i - 1 has completed
       auto wait_blocks_free = [&]() {
         if (i > 0) {
-          const int gl = kBwd ? 2 * (i - 1) : i * p.G - 1;         // its last group
+          const int gl = kBwd ? 2 * (i - 1) : i * G - 1;           // its last group
           mbar_wait(pdone_bar(gl & 1), ((uint32_t)(gl >> 1)) & 1u);
           tc_fence_after();
           if (warp == 4) EP_TRACE(i, 10);                          // epilogue: pooled MMAs of sample i - 1 complete
@@ -524,8 +581,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
         if (ew == 0 && lane == 0) *e_done = i + 1;
         if (!kBwd) {
-          if (i > 0) { const int gg = i * p.G - 1; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
-          for (int g = 0; g + 1 < p.G; ++g) { const int gg = i * p.G + g; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
+          if (i > 0) { const int gg = i * G - 1; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
+          for (int g = 0; g + 1 < G; ++g) { const int gg = i * G + g; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
         }
       } else if (!kBwd) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
@@ -551,7 +608,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const int m = j0 + q;                                  // warp-uniform
             const float mx = __shfl_sync(0xffffffffu, m < 32 ? mx_lo : mx_hi, m & 31);
             const bool on = valid && m < p.M;
-            if (on) __stcs(srow + (size_t)q * p.N, v[q]);
+            if (on && half == 0) __stcs(srow + (size_t)q * p.N, v[q]);
             v[q] = on ? __expf(v[q] - mx) : 0.f;
             if (blk && m < p.M) store_hilo(blk, m, tt, v[q]);
           }
@@ -586,7 +643,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
-          load_unit(acc, t, j0, v);
+          fetch_unit(t, j0, v);
           emit(t, j0, v, true);
         }
         fence_proxy_async();                                       // generic-proxy block writes -> visible to the MMAs
@@ -606,7 +663,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             if (m < SW)
               for (int w = 0; w < kEW; ++w) su += psum[w * SW + m];
             tot[(i & 1) * 64 + m] = su;
-            if (m < p.M) {
+            if (m < p.M && half == 0) {
               p.rmax[(size_t)b * p.M + m] = h ? mx_hi : mx_lo;
               p.rsum[(size_t)b * p.M + m] = su;
             }
@@ -615,8 +672,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
         // drains: the last group of the previous sample, then this sample's groups but the last (which completes
         // together with the next sample's logits)
-        if (i > 0) drain_group(b - gridDim.x, i - 1, p.G - 1);
-        for (int g = 0; g + 1 < p.G; ++g) drain_group(b, i, g);
+        if (i > 0) drain_group(b - ncta, i - 1, G - 1);
+        for (int g = 0; g + 1 < G; ++g) drain_group(b, i, g);
         if (warp == 4) EP_TRACE(i, 13);                            // epilogue: drains done
       } else {
         // ---- backward: dS = A (dA - delta), A recomputed from the saved logits and row statistics
@@ -632,7 +689,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             sv[q] = valid ? __ldcs(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
           }
           float v[16];
-          load_unit(acc, t, j0, v);
+          fetch_unit(t, j0, v);
           const int kb = n >> 6, tt = n & 63;
           uint8_t* blk = kb < p.nkb ? blk_gen + (size_t)kb * 2u * half_bytes : nullptr;
 #pragma unroll
@@ -658,27 +715,28 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       }
     }
     if (nmine > 0 && !kBwd) {
-      drain_group(blockIdx.x + (nmine - 1) * gridDim.x, nmine - 1, p.G - 1);
+      drain_group(cta + (nmine - 1) * ncta, nmine - 1, G - 1);
     } else if (nmine > 0) {
       // bwd: the query-gradient partial of this CTA, all slices
       const int gl = 2 * (nmine - 1);
       mbar_wait(pdone_bar(0), ((uint32_t)(gl >> 1)) & 1u);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_base + (uint32_t)p.pcol0;
-      for (int u = es; u < p.nsl * upt; u += kSub) {
+      for (int u = es; u < nslh * upt; u += kSub) {
         const int sl = u / upt, j0 = (u - sl * upt) << 4;
-        const int d = sl * 128 + wq * 32 + lane;
+        const int d = (sl_lo + sl) * 128 + wq * 32 + lane;
         uint32_t r[16];
         tmem_ld16(acc + (uint32_t)(sl * p.Mp + j0), r);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          if (j0 + q < p.M) p.out[((size_t)blockIdx.x * p.M + j0 + q) * p.D + d] = __uint_as_float(r[q]);
+          if (j0 + q < p.M) p.out[((size_t)cta * p.M + j0 + q) * p.D + d] = __uint_as_float(r[q]);
       }
     } else if (kBwd) {
       // a CTA without samples still owns a partial-gradient slice: zeros
-      for (size_t o = (size_t)(warp - 4) * 32 + lane; o < (size_t)p.M * p.D; o += 32 * kEW)
-        p.out[(size_t)blockIdx.x * p.M * p.D + o] = 0.f;
+      if (half == 0)
+        for (size_t o = (size_t)(warp - 4) * 32 + lane; o < (size_t)p.M * p.D; o += 32 * kEW)
+          p.out[(size_t)cta * p.M * p.D + o] = 0.f;
     }
   }
   tc_fence_before();
@@ -692,12 +750,13 @@ int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 struct FPlan {
   bool ok = false;
   int Mp, ntiles, nfull, tail_rows, nchunks, nkb, nsl, nL, nP, lbytes, nkp, pf, lead, nbuf, bufcols, pcol0, tmem_cols, qoff, toff, nslg, G, pbufcols;
-  int lsplit, lcolw, kl, last_rows;
+  int lsplit, lcolw, kl, last_rows, pair, nslA;
   size_t smem;
 };
 
-// L2 budget for the samples in flight (every CTA holds one sample plus the lead of the next between its two fetches)
-constexpr size_t kL2Budget = 100ull << 20;
+// L2 budget for the tokens alive between their two fetches (one sample plus the lead of the next per CTA or CTA pair):
+// measured, about half of the 126 MB is usable for this pattern (see "Pair mode" above); it only sizes the lead
+constexpr size_t kL2Budget = 58ull << 20;
 
 FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   FPlan pl;
@@ -714,6 +773,15 @@ FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   pl.nchunks = D / 64;
   pl.nkb = (N + 63) / 64;
   pl.nsl = D / 128;
+  // one CTA per sample, or a pair splitting D when that many whole samples would not stay in L2
+  const size_t sample = (size_t)N * D * 2;
+  // (pair mode is measured slower than one CTA per sample -- both CTAs run the whole softmax -- and stays behind
+  //  the developer knob: ep_set_debug bit 29)
+  const int fp = (g_debug >> 28) & 3;
+  pl.pair = fp == 2 && pl.nsl >= 2 && ctas >= 2;
+  pl.nslA = pl.pair ? (pl.nsl + 1) / 2 : pl.nsl;                  // d-slices of a CTA (the larger half)
+  const int live = pl.pair ? ctas / 2 : ctas;
+  const int nslc = pl.nslA, nchc = 2 * pl.nslA;
   pl.nkp = (pl.nkb + 1) / 2;                                      // tall bricks (128 tokens) per d-slice
   pl.kl = (N - (pl.nkp - 1) * 128 + 15) / 16;                     // 16-token k-steps of the last tall brick
   pl.last_rows = pl.kl * 16;
@@ -730,13 +798,13 @@ FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
     const int lcolw = lsplit ? pl.Mp : 2 * pl.Mp;
     const int left = 512 - nbuf * pl.ntiles * lcolw;
     if (bwd) {
-      if (left < pl.nsl * pl.Mp) continue;
-      pl.nslg = pl.nsl; pl.G = 1; pl.pbufcols = pl.nsl * pl.Mp;
+      if (left < nslc * pl.Mp) continue;
+      pl.nslg = nslc; pl.G = 1; pl.pbufcols = nslc * pl.Mp;
     } else {
       if (left < 2 * 2 * pl.Mp) continue;
-      pl.nslg = std::min(pl.nsl, left / (2 * 2 * pl.Mp));
-      pl.G = (pl.nsl + pl.nslg - 1) / pl.nslg;
-      pl.nslg = (pl.nsl + pl.G - 1) / pl.G;                       // balance the groups
+      pl.nslg = std::min(nslc, left / (2 * 2 * pl.Mp));
+      pl.G = (nslc + pl.nslg - 1) / pl.nslg;
+      pl.nslg = (nslc + pl.G - 1) / pl.G;                         // balance the groups
       pl.pbufcols = pl.nslg * 2 * pl.Mp;
     }
     pl.nbuf = nbuf; pl.lsplit = lsplit; pl.lcolw = lcolw;
@@ -756,12 +824,10 @@ FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   pl.smem = fixed + (size_t)pl.nP * kPBytes + (size_t)pl.nL * pl.lbytes;
   pl.pf = ((g_debug >> 22) & 7) ? ((g_debug >> 22) & 7) - 1 : 0;  // dev knob: bits 22-24 = L2 prefetch distance + 1
   // chunks of the next sample fetched before the first brick: enough to cover the epilogue, bounded by the L2 budget
-  const size_t sample = (size_t)N * D * 2;
-  pl.lead = std::min(((g_debug >> 16) & 15) ? ((g_debug >> 16) & 15) - 1 : 4, pl.nchunks / 2);   // dev knob: bits 16-19 = lead + 1
+  pl.lead = std::min(((g_debug >> 16) & 15) ? ((g_debug >> 16) & 15) - 1 : 4, nchc / 2);   // dev knob: bits 16-19 = lead + 1
   if (pl.nbuf == 1) pl.lead = 0;                                  // a lead needs the second logit buffer
   const size_t budget = kL2Budget + ((size_t)((g_debug >> 25) & 7) * 10 << 20);   // dev knob: bits 25-27 = +10 MB each
-  while (pl.lead > 0 && sample * ctas * (pl.nchunks + pl.lead) / pl.nchunks > budget) --pl.lead;
-  if (sample * ctas > kL2Budget) return pl;
+  while (pl.lead > 1 && sample * live * (nchc + pl.lead) / nchc > budget) --pl.lead;
   pl.ok = true;
   return pl;
 }
@@ -812,7 +878,7 @@ int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int 
   p.nchunks = pl.nchunks; p.nkb = pl.nkb; p.nsl = pl.nsl; p.nL = pl.nL; p.nP = pl.nP; p.lbytes = pl.lbytes; p.nkp = pl.nkp; p.pf = pl.pf;
   p.lead = pl.lead; p.nbuf = pl.nbuf;
   p.nslg = pl.nslg; p.G = pl.G; p.pbufcols = pl.pbufcols; p.lsplit = pl.lsplit; p.lcolw = pl.lcolw; p.kl = pl.kl;
-  p.last_rows = pl.last_rows;
+  p.last_rows = pl.last_rows; p.pair = pl.pair; p.nslA = pl.nslA;
   p.trace = (g_debug & 2048) ? 1 : 0; p.nomma = (g_debug & 4096) ? 1 : 0; p.noepi = (g_debug & 8192) ? 1 : 0;
   p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff; p.toff = pl.toff;
   if ((rc = set_smem(fused_kernel<kBwd>, pl.smem))) return rc;
@@ -834,27 +900,52 @@ bool fused_supported(int N, int D, int M) {
   return make_fplan(N, D, M, stream_sms(), false).ok && make_fplan(N, D, M, stream_sms(), true).ok;
 }
 
-// qhl: (J, D) bf16 hi/lo rows of the scaled queries
+// pair mode scratch: partial-logit exchange slots + flags (zero when the shape runs one CTA per sample)
+size_t fused_workspace_bytes(int N, int D, int M) {
+  const FPlan pl = make_fplan(N, D, M, kNumSMs, false);
+  if (!pl.ok) return 0;
+  return align_up((size_t)kNumSMs * 2 * pl.ntiles * pl.Mp * 128 * sizeof(float), 256) + align_up(kNumSMs * sizeof(int), 256);
+}
+
+namespace {
+// grid and pair-mode scratch of one launch
+int setup_launch(const FPlan& pl, int B, int N, int D, int M, void* xws, FParams* p, int* grid, cudaStream_t s) {
+  const int sms = stream_sms();
+  *grid = pl.pair ? 2 * std::min(B, sms / 2) : std::min(B, sms);
+  if (pl.pair) {
+    if (!xws) return EP_ERR_WORKSPACE;
+    const size_t xb = align_up((size_t)kNumSMs * 2 * pl.ntiles * pl.Mp * 128 * sizeof(float), 256);
+    p->xchg = (float*)xws;
+    p->flags = (int*)((char*)xws + xb);
+    EP_CUDA(cudaMemsetAsync(p->flags, 0, kNumSMs * sizeof(int), s));
+  }
+  return 0;
+}
+}  // namespace
+
+// qhl: (J, D) bf16 hi/lo rows of the scaled queries; xws: fused_workspace_bytes() of scratch
 int fused_pool_fwd(const void* x, const void* qhl, int J, int B, int N, int D, int M, float* P, float* S, float* rowmax,
-                   float* rowsum, int round_p, cudaStream_t s) {
-  const int grid = std::min(B, stream_sms());
-  const FPlan pl = make_fplan(N, D, M, grid, false);
+                   float* rowsum, int round_p, void* xws, cudaStream_t s) {
+  const FPlan pl = make_fplan(N, D, M, stream_sms(), false);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   FParams p{};
   p.S = S; p.rmax = rowmax; p.rsum = rowsum; p.out = P; p.round_out = round_p;
+  int grid, rc;
+  if ((rc = setup_launch(pl, B, N, D, M, xws, &p, &grid, s))) return rc;
   return launch_fused<false>(x, qhl, 0, J, B, N, D, M, pl, p, grid, s);
 }
 
-// dphl: (B, J, D) bf16 hi/lo rows of dP; part: [grid][M][D] partial query gradients (*groups_out = grid)
+// dphl: (B, J, D) bf16 hi/lo rows of dP; part: [groups][M][D] partial query gradients (*groups_out = CTAs or CTA pairs)
 int fused_pool_bwd(const void* x, const void* dphl, int J, int B, int N, int D, int M, const float* S, const float* rowmax,
-                   const float* rowsum, const float* delta, float* part, int* groups_out, cudaStream_t s) {
-  const int grid = std::min(B, stream_sms());
-  const FPlan pl = make_fplan(N, D, M, grid, true);
+                   const float* rowsum, const float* delta, float* part, int* groups_out, void* xws, cudaStream_t s) {
+  const FPlan pl = make_fplan(N, D, M, stream_sms(), true);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   FParams p{};
   p.S = const_cast<float*>(S); p.rmax = const_cast<float*>(rowmax); p.rsum = const_cast<float*>(rowsum);
   p.delta = delta; p.out = part;
-  *groups_out = grid;
+  int grid, rc;
+  if ((rc = setup_launch(pl, B, N, D, M, xws, &p, &grid, s))) return rc;
+  *groups_out = pl.pair ? grid / 2 : grid;
   return launch_fused<true>(x, dphl, 1, J, B, N, D, M, pl, p, grid, s);
 }
 

@@ -766,7 +766,7 @@ Plan make_plan(int N, int D, int M) {
 }
 
 struct Ws100 {
-  size_t qhl, S_unused, dphl, dS, part, total;
+  size_t qhl, S_unused, dphl, dS, part, fused, total;
 };
 Ws100 carve100(int B, int N, int D, int M, const Plan& pl) {
   Ws100 w;
@@ -775,6 +775,7 @@ Ws100 carve100(int B, int N, int D, int M, const Plan& pl) {
   w.dphl = off; off += align_up((size_t)B * pl.J * D * 2, 1024);
   w.dS = off;   off += align_up((size_t)B * pl.nkb * pl.J * 128, 1024);   // operand blocks (exp(S - max) / dS)
   w.part = off; off += align_up((size_t)kNumSMs * M * D * 4, 256);
+  w.fused = off; off += align_up(fused_workspace_bytes(N, D, M), 256);   // pair-mode scratch of the one-pass kernels
   w.S_unused = 0;
   w.total = off;
   return w;
@@ -862,7 +863,7 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   tm.mark("split_q");
   // one-pass kernel: logits, softmax and pooled tokens of a sample without leaving the SM (ep_fused_sm100.cu)
   if (attn == nullptr && P != nullptr && !(g_debug & 1024) && fused_supported(N, D, M)) {
-    rc = fused_pool_fwd(x, qhl, pl.J, B, N, D, M, P, S, rowmax, rowsum, round_p, s);
+    rc = fused_pool_fwd(x, qhl, pl.J, B, N, D, M, P, S, rowmax, rowsum, round_p, (char*)ws + w.fused, s);
     tm.mark("fused fwd");
     return rc;
   }
@@ -921,7 +922,7 @@ int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int
   int groups = 0;
   if (ndelta == 1 && !(g_debug & 1024) && fused_supported(N, D, M)) {
     // one-pass kernel: dA, dS and the query gradient of a sample without leaving the SM (ep_fused_sm100.cu)
-    if ((rc = fused_pool_bwd(x, dphl, pl.J, B, N, D, M, S, rowmax, rowsum, delta, part, &groups, s))) return rc;
+    if ((rc = fused_pool_bwd(x, dphl, pl.J, B, N, D, M, S, rowmax, rowsum, delta, part, &groups, (char*)ws + w.fused, s))) return rc;
     tm.mark("fused bwd");
   } else {
     if ((rc = launch_ks<1>(x, dphl, 1, B, N, D, M, pl, nullptr, blocks, S, rowmax, rowsum, delta, ndelta, s))) return rc;

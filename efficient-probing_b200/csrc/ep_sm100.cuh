@@ -23,8 +23,9 @@ int make_tmap_bf16(::CUtensorMap_st* m, const void* base, int rank, const uint64
 // one-pass fused kernels (ep_fused_sm100.cu): tokens cross HBM once per direction, second fetch from L2
 bool fused_supported(int N, int D, int M);
 int fused_trace_fetch(long long* host_out, int n);
+size_t fused_workspace_bytes(int N, int D, int M);
 int fused_pool_fwd(const void* x, const void* qhl, int J, int B, int N, int D, int M, float* P, float* S, float* rowmax,
-                   float* rowsum, int round_p, cudaStream_t s);
+                   float* rowsum, int round_p, void* xws, cudaStream_t s);
 int fused_pool_bwd(const void* x, const void* dphl, int J, int B, int N, int D, int M, const float* S, const float* rowmax,
-                   const float* rowsum, const float* delta, float* part, int* groups_out, cudaStream_t s);
+                   const float* rowsum, const float* delta, float* part, int* groups_out, void* xws, cudaStream_t s);
 }  // namespace ep
