@@ -126,19 +126,30 @@ def cpu_reference_step(cfg, M, sample_B, iters, warmup, threads=None):
     return sample_B * N / sec, sec, cores
 
 
+def config_dict(args, cfg, world, comm_sms=None, extra=None):
+    """`config` of the JSON line -- the same keys and values for our arm and the reference arm."""
+    B, N, D, K, M = cfg["B"], cfg["N"], cfg["D"], cfg["K"], args.queries
+    c = {"workload": f"EP head (M={M}) on {cfg['name']}, per-GPU batch {B}, {K} classes, fwd+bwd+allreduce+LARS",
+         "per_gpu_batch": B, "global_batch": B * world, "tokens": N, "dim": D, "queries": M, "classes": K,
+         "parallelism": f"dp{world}"}
+    c.update(extra or {})
+    return c
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = args.cpu_sample
+    # the same step as our arm: the config's full per-GPU batch on the host cores (about 0.8 s per step for c2 on a
+    # 2-socket host); --cpu-sample bounds it for the largest configs
+    sample_B = args.cpu_sample or cfg["B"]
     val, sec, cores = cpu_reference_step(cfg, args.queries, sample_B, args.steps, args.warmup)
     sample = (f"{sample_B} of {cfg['B']} samples per step of the same workload, reference formulation "
-              f"(value projection on every token) fwd+bwd+LARS, torch fp32, {cores} threads")
+              f"(value projection on every token) fwd+bwd+LARS, torch fp32, {cores} threads; rank 0 only")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"EP head (M={args.queries}) on {cfg['name']}, 1000 classes, fwd+bwd+LARS",
-                       "sample_batch": sample_B, "tokens": cfg["N"], "dim": cfg["D"], "queries": args.queries},
+            "config": config_dict(args, cfg, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -172,7 +183,8 @@ def main():
     ap.add_argument("--queries", type=int, default=32)
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--pool", type=int, default=8, help="distinct resident batches cycled through")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="samples per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="samples per CPU step (0 = reference arm: the full per-GPU batch; cpu_baseline leg: 64)")
     ap.add_argument("--comm-sms", type=int, default=-1,
                     help="SMs reserved for the overlapped all-reduce (N > 1); -1 = the trainer's default for N")
     ap.add_argument("--no-graph", action="store_true")
@@ -229,7 +241,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput: W warm-up + exactly K timed steps ----------------
-    for i in range(max(args.warmup, args.pool)):                 # every pool slot's graph exists before timing
+    for i in range(args.pool):                                   # set-up: capture every pool slot's graph (no training)
+        tr.prepare(pool_x[i], pool_y[i])
+    for i in range(args.warmup):
         tr.train_step(pool_x[i % args.pool], pool_y[i % args.pool])
     barrier()
     sampler = ClockSampler(local)
@@ -251,6 +265,16 @@ def main():
     ms_per_step = total_ms / args.steps
     value = B * N * world * args.steps / (total_ms * 1e-3)
     loss = tr.mean_loss()
+    # replicas must still be identical: max |p - p_rank0| over all parameters and ranks
+    replica_diff = None
+    if world > 1:
+        dmax = torch.zeros(1, device=dev)
+        for prm in tr.params:
+            ref = prm.detach().clone()
+            dist.broadcast(ref, src=0)
+            dmax = torch.maximum(dmax, (prm.detach() - ref).abs().max().reshape(1))
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        replica_diff = float(dmax)
 
     # ---------------- end to end from pinned host buffers ----------------
     hx = [pool_x[i].cpu().pin_memory() for i in range(2)]
@@ -303,7 +327,7 @@ def main():
     for nm, us in E._lib.kernel_timings():
         agg.setdefault(nm, []).append(us)
     kernels = {k: sum(v) / len(v) for k, v in agg.items()}
-    streaming = {k: v for k, v in kernels.items() if k.startswith(("ks<", "kp<", "pool_"))}
+    streaming = {k: v for k, v in kernels.items() if k.startswith(("ks<", "kp<", "pool_", "fused "))}
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -326,13 +350,12 @@ def main():
             dist.destroy_process_group()
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, args.pool), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"EP head (M={M}) on {cfg['name']}, per-GPU batch {B}, {K} classes, "
-                                   f"fwd+bwd+allreduce+LARS", "per_gpu_batch": B, "global_batch": B * world,
-                       "tokens": N, "dim": D, "queries": M, "classes": K, "parallelism": f"dp{world}", "comm_sms": tr.comm_sms,
-                       "l2": f"inputs larger than L2: {args.pool} resident batches x {alg_bytes / 1e6:.0f} MB cycled",
-                       "cuda_graph": not args.no_graph, "kernel_family": fam},
+            "config": config_dict(args, cfg, world),
+            "run": {"comm_sms": tr.comm_sms, "cuda_graph": not args.no_graph, "kernel_family": fam,
+                    "l2": f"inputs larger than L2: {args.pool} resident batches x {alg_bytes / 1e6:.0f} MB cycled",
+                    "replica_max_abs_diff": replica_diff},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ms2) / e2e_steps},
@@ -344,7 +367,7 @@ def main():
             "mean_loss": loss}
     if not args.no_cpu_baseline:
         try:
-            sb = args.cpu_sample
+            sb = args.cpu_sample or 64
             val, sec, cores = cpu_reference_step(cfg, M, sb, iters=8, warmup=2)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sb} of {B} samples of the same workload per step, reference "

@@ -23,9 +23,21 @@
 namespace ep {
 
 extern unsigned long long g_launch_count;     // kernels launched by this library in this process
-constexpr int kNumSMs = 148;
+constexpr int kNumSMs = 148;           // B200; upper bound used for workspace sizing
 extern int g_sm_limit;                 // ep_set_sm_limit: CTAs the persistent token-streaming kernels may launch (0 = all SMs)
-inline int stream_sms() { return g_sm_limit > 0 && g_sm_limit < kNumSMs ? g_sm_limit : kNumSMs; }
+// SMs of the current device (queried once), never more than the workspace bound
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v < kNumSMs ? v : kNumSMs;
+    else
+      n = kNumSMs;
+  }
+  return n;
+}
+inline int stream_sms() { const int n = num_sms(); return g_sm_limit > 0 && g_sm_limit < n ? g_sm_limit : n; }
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -259,7 +259,10 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       long long t_wait = 0, t_begin = clock64();
       for (int i = 0; i < nmine; ++i) {
         const int b = cta + i * ncta;
-        for (int sl = sl_lo; sl < sl_lo + nslh; ++sl)
+        // slices in DESCENDING order: the logit phase fetched d ascending, so the most recently fetched lines -- the
+        // ones most likely still in L2 -- are re-read first (under an LRU-like policy, re-reading in fetch order
+        // would miss everything as soon as the live set exceeds the capacity)
+        for (int sl = sl_lo + nslh - 1; sl >= sl_lo; --sl)
           for (int kp = 0; kp < p.nkp; ++kp) {
             const long long t0 = p.trace ? clock64() : 0;
             mbar_wait(pempty_bar(s), ph ^ 1u);
@@ -418,7 +421,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (h * 32 + lane < p.M) invl[h] = 1.f / tot[(i & 1) * 64 + h * 32 + lane];
       for (int u = es; u < gs * upt; u += kSub) {
         const int slg = u / upt, j0 = (u - slg * upt) << 4;
-        const int d = (sl_lo + g * p.nslg + slg) * 128 + wq * 32 + lane;
+        const int d = (sl_lo + nslh - 1 - (g * p.nslg + slg)) * 128 + wq * 32 + lane;   // pooled phase walks the slices downwards
         uint32_t rh[16], rl[16];
         tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + j0), rh);
         tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + p.Mp + j0), rl);
@@ -724,7 +727,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const uint32_t acc = tmem_base + lane_base + (uint32_t)p.pcol0;
       for (int u = es; u < nslh * upt; u += kSub) {
         const int sl = u / upt, j0 = (u - sl * upt) << 4;
-        const int d = (sl_lo + sl) * 128 + wq * 32 + lane;
+        const int d = (sl_lo + nslh - 1 - sl) * 128 + wq * 32 + lane;   // accumulator sl holds the sl-th slice from the top
         uint32_t r[16];
         tmem_ld16(acc + (uint32_t)(sl * p.Mp + j0), r);
         tmem_ld_wait();

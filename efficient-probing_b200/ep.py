@@ -95,6 +95,11 @@ class EPPoolFunction(torch.autograd.Function):
                                    d_cls.data_ptr(), d_w.data_ptr(), _lib.ptr(d_b), _lib.ptr(dx), ws.data_ptr(),
                                    ws.numel(), _lib.stream_ptr(dev))
             else:
+                # ep_bwd re-derives the layout of the saved P from the process-wide kernel / GEMM mode: refuse to
+                # read it back under another mode than the one the forward wrote it in
+                if lib.ep_pooled_layout(_lib.x_dtype_code(x), B, N, D, M, d_out) != p_layout:
+                    raise RuntimeError("ep_set_kernel_mode / ep_set_gemm_mode changed between forward and backward: "
+                                       "the saved pooled tokens are in the other layout")
                 rc = lib.ep_bwd(x.data_ptr(), _lib.x_dtype_code(x), cls32.data_ptr(), w32.data_ptr(), scale,
                                 B, N, D, M, d_out, S.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), P.data_ptr(),
                                 out.data_ptr(), _lib.ptr(b32), g.data_ptr(),

@@ -48,10 +48,22 @@ def load_head(obj, device=None):
     return (head.to(device) if device is not None else head), meta
 
 
-def save_checkpoint(path, head, optimizer_state=None, epoch=0, args=None, test_stats=None):
-    """Write the head-only checkpoint of util/misc.py:304-332 (what ``--resume`` / ``--auto_resume`` read)."""
+def grad_scaler_state(scale: float = 65536.0) -> dict:
+    """State dict of a fresh ``torch.cuda.amp.GradScaler`` -- what ``NativeScalerWithGradNormCount.state_dict()``
+    (util/misc.py:283-286) returns and ``load_model`` (util/misc.py:385) feeds to ``loss_scaler.load_state_dict``.
+    The bf16 / fp32 step of this package needs no loss scaling; the entry exists so the reference can resume."""
+    return {"scale": float(scale), "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 0}
+
+
+def save_checkpoint(path, head, optimizer_state, epoch=0, args=None, test_stats=None, scaler_state=None):
+    """Write the head-only checkpoint of util/misc.py:304-332 (what ``--resume`` / ``--auto_resume`` read).
+    ``optimizer_state``: ``EPHeadTrainer.optimizer_state_dict()`` or a torch optimizer's ``state_dict()`` -- required,
+    because the reference's ``load_model`` (util/misc.py:381-385) calls ``optimizer.load_state_dict`` on it."""
+    if not isinstance(optimizer_state, dict) or "state" not in optimizer_state or "param_groups" not in optimizer_state:
+        raise ValueError("optimizer_state must be an optimizer state_dict ({'state': ..., 'param_groups': ...})")
     torch.save({"saved_module": "head", "model": {k: v.detach().cpu() for k, v in head.state_dict().items()},
-                "optimizer": optimizer_state, "epoch": epoch, "scaler": None, "args": args,
+                "optimizer": optimizer_state, "epoch": epoch,
+                "scaler": dict(scaler_state) if scaler_state is not None else grad_scaler_state(), "args": args,
                 "test_stats": test_stats}, path)
 
 

@@ -76,6 +76,8 @@ class LARS(torch.optim.Optimizer):
                 _lib.require_cuda(p, "LARS parameter")
                 if p.dtype != torch.float32 or p.grad.dtype != torch.float32:
                     raise TypeError("LARS (ep_lars_step) handles fp32 parameters and gradients only")
+                if not p.is_contiguous():     # the kernel updates in place: a contiguous copy would swallow the step
+                    raise ValueError("LARS (ep_lars_step) updates parameters in place and needs them contiguous")
                 if "mu" not in self.state[p]:
                     self.state[p]["mu"] = torch.zeros_like(p)
             dev = todo[0].device
@@ -88,7 +90,7 @@ class LARS(torch.optim.Optimizer):
                                      dtype=torch.float32), non_blocking=True)
             for i in range(0, len(todo), 8):
                 chunk = todo[i:i + 8]
-                lars_launch([p.data if p.is_contiguous() else p.data.contiguous() for p in chunk],
+                lars_launch([p.data for p in chunk],
                             [p.grad.contiguous() for p in chunk], [self.state[p]["mu"] for p in chunk],
                             [p.ndim > 1 for p in chunk], hyper, scratch)
 

@@ -40,14 +40,24 @@ class EPHeadTrainer:
                  weight_decay: float = 0.0, momentum: float = 0.9, trust_coefficient: float = 0.001,
                  x_dtype: torch.dtype = torch.bfloat16, process_group=None, use_graph: bool = True,
                  overlap_comm: bool = True, optimizer: str = "lars", betas=(0.9, 0.999), eps: float = 1e-8,
-                 accum_iter: int = 1, comm_sms: Optional[int] = None):
+                 accum_iter: int = 1, comm_sms: Optional[int] = None, broadcast_buffers: str = "eval"):
         """comm_sms: SMs left free for the overlapped gradient all-reduce while the token-streaming half of the
         backward pass runs (multi-GPU only; pair it with NCCL_MAX_CTAS <= comm_sms set before the process group is
         created -- bench.py does -- so the collective's CTAs fit there).  None = default_comm_sms(world): measured
         on B200/NVSwitch, c2: 8 GPUs 0.827 ms/step with 0, 0.789 with 8, 0.767 with 16; 2 GPUs are fastest with 0.
         optimizer: "lars" (util/lars.py, the published protocol), "adamw" (torch.optim.AdamW defaults) or "sgd"
         (torch.optim.SGD, momentum as given) -- the three main_linprobe.py:403-408 can build.
-        accum_iter: gradient accumulation as engine_finetune.py:72-77 (loss / accum_iter, optimizer every k-th call)."""
+        accum_iter: gradient accumulation as engine_finetune.py:72-77 (loss / accum_iter, optimizer every k-th call).
+        Multi-GPU replicas are made identical here, as DistributedDataParallel's constructor does
+        (main_linprobe.py:581-583): rank 0's parameters and BatchNorm buffers are broadcast to every rank (the
+        reference seeds each rank with seed + rank, main_linprobe.py:517, and relies on exactly that).
+        broadcast_buffers: DDP(broadcast_buffers=True) replaces every rank's BatchNorm running statistics by rank 0's
+        before each forward (batch statistics stay per GPU: no SyncBN).  In training mode nothing reads them but
+        their own update, so the only observable effect is which statistics evaluation and checkpoints see:
+        "eval" (default) broadcasts rank 0's before eval_logits / state export -- same predictions, no per-step
+        message; "step" also broadcasts before every training step, as DDP literally does; "off" never."""
+        if broadcast_buffers not in ("eval", "step", "off"):
+            raise ValueError("broadcast_buffers must be 'eval', 'step' or 'off'")
         if optimizer not in ("lars", "adamw", "sgd"):
             raise ValueError("optimizer must be 'lars', 'adamw' or 'sgd'")
         self.optimizer, self.betas, self.eps_opt, self.accum_iter = optimizer, betas, eps, max(1, int(accum_iter))
@@ -74,6 +84,7 @@ class EPHeadTrainer:
         self.use_graph = use_graph
         self.overlap_comm = overlap_comm and self.world > 1
         self.comm_sms = (default_comm_sms(self.world) if comm_sms is None else int(comm_sms)) if self.overlap_comm else 0
+        self.broadcast_buffers = broadcast_buffers if self.world > 1 else "off"
 
         f32 = dict(dtype=torch.float32, device=dev)
         B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
@@ -126,6 +137,12 @@ class EPHeadTrainer:
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
         self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
+        # BatchNorm running statistics as two views of one flat tensor, so that DDP's buffer broadcast is one message
+        self.bn_flat = torch.cat([bn.running_mean.detach().reshape(-1), bn.running_var.detach().reshape(-1)]).contiguous()
+        bn.running_mean.data = self.bn_flat[:Dp]
+        bn.running_var.data = self.bn_flat[Dp:]
+        if self.world > 1:
+            self.sync_replicas()
         self.side_stream = torch.cuda.Stream(device=dev)
         self._cx, self._ct = self.x, self.targets           # the batch the next launch sequence reads
         self._registered = {}                               # (x ptr, targets ptr) -> (x, targets) kept alive
@@ -134,6 +151,28 @@ class EPHeadTrainer:
         self.launches_per_step = None
         # pinned staging for the host-buffer API
         self._hx = self._ht = self._hloss = None
+
+    @torch.no_grad()
+    def sync_replicas(self):
+        """Rank 0's parameters, BatchNorm buffers and optimizer state -> every rank (DDP's constructor broadcast;
+        call it again after load_state_dict / load_optimizer_state_dict on rank 0 alone)."""
+        if self.world == 1:
+            return
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        for t in self.params + self.mus + (self.sq or []) + [self.bn_flat, self.bn.num_batches_tracked]:
+            dist.broadcast(t.data, src=src, group=self.group)
+        steps = torch.tensor([self.opt_steps], dtype=torch.int64, device=self.dev)
+        dist.broadcast(steps, src=src, group=self.group)
+        self.opt_steps = int(steps.item())
+        if self.optimizer != "lars":
+            self._write_hyper()
+
+    def _broadcast_buffers(self):
+        """Rank 0's BatchNorm running statistics -> every rank (main_linprobe.py:582, DDP's buffer broadcast)."""
+        if self.world == 1 or self.broadcast_buffers == "off":
+            return
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(self.bn_flat, src=src, group=self.group)
 
     # ------------------------------------------------------------------ one step, stream-ordered
     def _forward(self, training: bool):
@@ -271,15 +310,8 @@ class EPHeadTrainer:
         self._exchange_rest()
         self._part3()
 
-    def _run(self):
-        if not self.use_graph:
-            if self.launches_per_step is None:
-                n0 = self.lib.ep_launch_count()
-                self._step_body()
-                self.launches_per_step = int(self.lib.ep_launch_count() - n0)
-            else:
-                self._step_body()
-            return
+    def _ensure_graphs(self):
+        """Captured graphs of the step for the current batch slot (built on first use)."""
         key = (self._cx.data_ptr(), self._ct.data_ptr())
         graphs = self.graphs.get(key)
         if graphs is None:
@@ -306,6 +338,18 @@ class EPHeadTrainer:
                     part()
                 graphs.append(g)
             self.graphs[key] = graphs
+        return graphs
+
+    def _run(self):
+        if not self.use_graph:
+            if self.launches_per_step is None:
+                n0 = self.lib.ep_launch_count()
+                self._step_body()
+                self.launches_per_step = int(self.lib.ep_launch_count() - n0)
+            else:
+                self._step_body()
+            return
+        graphs = self._ensure_graphs()
         if self.world == 1:
             graphs[0].replay()
         else:
@@ -314,6 +358,18 @@ class EPHeadTrainer:
             graphs[1].replay()
             self._exchange_rest()
             graphs[2].replay()
+
+    @torch.no_grad()
+    def prepare(self, x: torch.Tensor, targets: torch.Tensor):
+        """Set-up for a registered batch slot without training on it: build (capture) the step's CUDA graph now, so the
+        first train_step on it is already a replay.  Parameters, optimizer state and meters are left untouched."""
+        key = (x.data_ptr(), targets.data_ptr())
+        if key not in self._registered:
+            self.register_batch(x, targets)
+        if not self.use_graph:
+            return
+        self._cx, self._ct = self._registered[key]
+        self._ensure_graphs()
 
     def _snapshot(self):
         bn = self.bn
@@ -365,6 +421,8 @@ class EPHeadTrainer:
                 self.x.copy_(x, non_blocking=True)
             if targets.data_ptr() != self.targets.data_ptr():
                 self.targets.copy_(targets, non_blocking=True)
+        if self.broadcast_buffers == "step":
+            self._broadcast_buffers()
         self._run()
         self._after_run()
         self.steps += 1
@@ -422,6 +480,8 @@ class EPHeadTrainer:
             self._slots[slot][1].copy_(th, non_blocking=True)
         self._prefetched = None
         self._cx, self._ct = self._slots[slot]
+        if self.broadcast_buffers == "step":
+            self._broadcast_buffers()
         self._run()
         self._after_run()
         self.steps += 1
@@ -439,15 +499,22 @@ class EPHeadTrainer:
 
     @torch.no_grad()
     def eval_logits(self, x: torch.Tensor) -> torch.Tensor:
-        """model.eval() forward (BatchNorm on running statistics), engine_finetune.py:106-166."""
+        """model.eval() forward (BatchNorm on running statistics), engine_finetune.py:106-166.  Accepts any batch of
+        1..B samples (the reference's validation loader keeps its last partial batch); returns (b, K) logits."""
+        if x.dim() != 3 or tuple(x.shape[1:]) != (self.N, self.D) or not 1 <= x.shape[0] <= self.B or x.dtype != self.x_dtype:
+            raise ValueError(f"x must be (b <= {self.B}, {self.N}, {self.D}) {self.x_dtype}, got {tuple(x.shape)} {x.dtype}")
+        b = x.shape[0]
+        self._broadcast_buffers()             # every rank evaluates on rank 0's running statistics, as under DDP
         self._cx = self.x
-        self.x.copy_(x, non_blocking=True)
+        self.x[:b].copy_(x, non_blocking=True)
+        if b < self.B:
+            self.x[b:].zero_()                # samples are independent in eval mode: the padding rows are dropped below
         self.lib.ep_set_gemm_mode(1)          # evaluation: fp32 contractions, predictions must not move
         try:
             self._forward(training=False)
         finally:
             self.lib.ep_set_gemm_mode(0)
-        return self.logits.clone()
+        return self.logits[:b].clone()
 
     def mean_loss(self) -> float:
         """Mean of the per-step losses since the last reset (one D2H sync, on demand)."""

@@ -8,8 +8,13 @@
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named *_host;
  *   - the library never allocates, frees or retains device memory: outputs and workspace are
  *     caller-owned (PyTorch caching allocator on the reference side);
- *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
- *     synchronisation and is CUDA-graph capturable; no global mutable state, re-entrant;
+ *   - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation, is CUDA-graph capturable and keeps no state between calls.  The developer
+ *     knobs (ep_set_kernel_mode, ep_set_gemm_mode, ep_set_sm_limit, ep_set_debug) are PROCESS-WIDE
+ *     settings read when a call is made: set them before capturing a graph (their value is baked
+ *     into it), not concurrently with calls on other threads, and do not change the kernel / GEMM
+ *     mode between a forward and its backward (ep_pooled_layout tells which layout of P a mode
+ *     writes).  ep_set_debug(32) timers synchronise the stream at the end of a call (developer aid);
  *   - return 0 on success, a NEGATIVE ep_status for rejected arguments, a POSITIVE value for a
  *     cudaError_t raised by a launch.  There is no CPU fallback of any kind.
  *   - tensors are contiguous row-major; token tensors x are (B, N, D) bf16 (EP_DTYPE_BF16, the fast

@@ -1,6 +1,8 @@
 """CPU tests of the rows either side of the hot path: token cache format (tools/dump_tokens.py) and head files
 (util/misc.py:304-332, tools/export_ep_heads.py:125)."""
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -96,3 +98,60 @@ def test_batch_gather_across_shards_matches_row_lookup(tmp_path):
             sh = int(np.searchsorted(st.offsets, i, side="right") - 1)
             k = i - int(st.offsets[sh])
             assert torch.equal(st._hx[0][j], shards[sh].tokens[k]) and int(st._hy[0][j]) == int(shards[sh].labels[k])
+
+
+def test_checkpoint_resumes_through_reference_load_model(tmp_path):
+    """The checkpoint save_checkpoint writes goes through the reference's own ``util.misc.load_model``
+    (util/misc.py:335-393): head weights into ``model.head``, the optimizer state into the reference LARS, the
+    scaler entry into a GradScaler.  Needs the reference checkout (build container only)."""
+    import argparse
+    import importlib.util
+    import sys
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "util", "misc.py")):
+        pytest.skip("reference checkout not present")
+    sys.dont_write_bytecode = True
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    try:
+        misc = load("_ref_misc", os.path.join(ref, "util", "misc.py"))
+        lars = load("_ref_lars", os.path.join(ref, "util", "lars.py"))
+    except Exception as e:                                    # a dependency of util/misc.py missing in this image
+        pytest.skip(f"reference util modules not importable here: {e}")
+    torch.manual_seed(0)
+    head = E.make_ep_head(64, num_queries=8, nb_classes=10)
+    mu = {i: {"mu": torch.full_like(p, 0.25 * (i + 1))} for i, p in enumerate(head.parameters())}
+    opt_state = {"state": mu, "param_groups": [{"lr": 0.4, "weight_decay": 0.0, "momentum": 0.9, "trust_coefficient": 0.001,
+                                                "params": list(range(len(mu)))}]}
+    path = str(tmp_path / "checkpoint-3.pth")
+    E.save_checkpoint(path, head, opt_state, epoch=3, test_stats={"acc1": 1.0})
+    with pytest.raises(ValueError):
+        E.save_checkpoint(path + ".bad", head, None)
+
+    class Model(torch.nn.Module):                             # what main_linprobe.py hands to load_model: a model with .head
+        def __init__(self):
+            super().__init__()
+            self.backbone = torch.nn.Linear(4, 4)
+            torch.manual_seed(1)
+            self.head = E.make_ep_head(64, num_queries=8, nb_classes=10)
+    model = Model()
+    optimizer = lars.LARS(model.head.parameters(), lr=0.1)
+
+    class Scaler:                                             # NativeScalerWithGradNormCount.load_state_dict (util/misc.py:285-286)
+        def __init__(self):
+            self._scaler = torch.amp.GradScaler("cpu", enabled=True)
+
+        def load_state_dict(self, sd):
+            self._scaler.load_state_dict(sd)
+    args = argparse.Namespace(resume=path, start_epoch=0, eval=False, knn_eval=False)
+    stats = misc.load_model(args, model, optimizer=optimizer, loss_scaler=Scaler())
+    assert stats == {"acc1": 1.0} and args.start_epoch == 4
+    for (k, a), (_, b) in zip(head.state_dict().items(), model.head.state_dict().items()):
+        assert torch.equal(a, b), k
+    for i, p in enumerate(model.head.parameters()):
+        assert torch.equal(optimizer.state[p]["mu"], mu[i]["mu"])
+    assert optimizer.param_groups[0]["lr"] == 0.4
