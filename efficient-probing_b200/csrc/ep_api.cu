@@ -379,6 +379,21 @@ extern "C" int ep_attention_maps(const void* x, int x_dtype, const float* cls_to
   if (!attn) return EP_ERR_NULL;
   const size_t need = align_up((size_t)2 * B * M * sizeof(float), 256);
   if (!workspace || workspace_bytes < need) return EP_ERR_WORKSPACE;
+  // tcgen05 route (logit kernel + row statistics writing the normalised map) when the shape is covered and the
+  // caller's workspace is the full ep_workspace_bytes() one: the logits go to its dP region
+  {
+    int frc = 0;
+    const Ws w = carve(B, N, D, M);
+    if (use_sm100(x_dtype, B, N, D, M, &frc) && workspace_bytes >= w.total && (size_t)N <= (size_t)D &&
+        (size_t)2 * B * M <= (size_t)kDqSlots * M * D) {
+      float* S = (float*)((char*)workspace + w.dP);
+      float* stats = (float*)((char*)workspace + w.slots);
+      t_last_family = 2;
+      return sm100_pool_fwd(x, cls_token, scale, B, N, D, M, nullptr, S, stats, stats + (size_t)B * M, attn, 0,
+                            (char*)workspace + w.sm100, (cudaStream_t)stream);
+    }
+    if (frc) return frc;
+  }
   float* rowmax = (float*)workspace;
   float* rowsum = rowmax + (size_t)B * M;
   t_last_family = 1;

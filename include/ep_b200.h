@@ -149,7 +149,9 @@ int ep_bwd_ex(const void* x, int x_dtype, const float* cls_token, int cls_batche
               float* d_cls_token, float* d_v_w, float* d_v_b, void* dx,
               void* workspace, size_t workspace_bytes, void* stream);
 
-/* tools/ep_attention_maps.py:51-58 for a batch: attn[b] = softmax(scale * cls_token @ x[b]^T), (B, M, N). */
+/* tools/ep_attention_maps.py:51-58 for a batch: attn[b] = softmax(scale * cls_token @ x[b]^T), (B, M, N).
+ * With a workspace of ep_workspace_bytes() and a shape the tcgen05 kernels cover (bf16 tokens, D % 128 == 0, N <= D)
+ * the logits come from the tensor-core kernel; otherwise (or with the small workspace) from the general one. */
 int ep_attention_maps(const void* x, int x_dtype, const float* cls_token, float scale,
                       int B, int N, int D, int M, float* attn,
                       void* workspace, size_t workspace_bytes, void* stream);
