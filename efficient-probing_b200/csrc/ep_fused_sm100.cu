@@ -74,7 +74,7 @@ constexpr int kCache = 2;              // logit units a warp keeps in registers 
 
 // developer trace (ep_set_debug bit 11): clock64 stamps of CTA 0's MMA warp and epilogue warp 4, 16 stamps x 8 samples
 __device__ long long g_trace[128];
-#define EP_TRACE(i, k) do { if (p.trace && blockIdx.x == 0 && (i) < 8 && lane == 0) g_trace[(i) * 16 + (k)] = clock64(); } while (0)
+#define EP_TRACE(i, k) do { if (trace && blockIdx.x == 0 && (i) < 8 && lane == 0) g_trace[(i) * 16 + (k)] = clock64(); } while (0)
 
 struct FParams {
   int B, N, D, M, Mp;                  // Mp = M rounded up to 16: UMMA N, accumulator columns per tile / slice
@@ -141,10 +141,18 @@ __device__ __forceinline__ uint32_t blk_off(uint32_t m, uint32_t t) {
   return m * 128u + (((t >> 3) ^ (m & 7u)) << 4) + (t & 7u) * 2u;
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 constexpr int kPBytes = 2 * kSlotBytes;   // P ring stage: a tall brick [128 tokens x 128 d] as two 64-d halves
 
 // kBwd = false: forward (logits, softmax, pooled tokens).  kBwd = true: backward (dA, dS, query gradient).
-template <bool kBwd>
+// kDev = true compiles the developer knobs in (trace stamps, noepi / nomma timing experiments, pair mode)
+template <bool kBwd, bool kDev>
 __global__ void __launch_bounds__(kThreadsF, 1)
 fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x1,
              const __grid_constant__ CUtensorMap tm_xt, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bl,
@@ -176,6 +184,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   volatile int* p_issued = reinterpret_cast<volatile int*>(gen + (misc + 64u - ring));
   volatile int* e_done = reinterpret_cast<volatile int*>(gen + (misc + 68u - ring));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool trace = kDev && p.trace, noepi = kDev && p.noepi, nomma = kDev && p.nomma, pair = kDev && p.pair;
 
   if (threadIdx.x == 0) {
     for (int q = 0; q < 4; ++q) { mbar_init(lfull_bar(q), 1); mbar_init(lempty_bar(q), 1); mbar_init(pfull_bar(q), 1); mbar_init(pempty_bar(q), 1); }
@@ -198,9 +207,9 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // this CTA's samples, d-chunks [c_lo, c_lo + nch) and d-slices [sl_lo, sl_lo + nslh)
-  const int cta = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int half = p.pair ? (int)(blockIdx.x & 1) : 0;
-  const int sl_lo = half ? p.nslA : 0, nslh = p.pair ? (half ? p.nsl - p.nslA : p.nslA) : p.nsl;
+  const int cta = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int half = pair ? (int)(blockIdx.x & 1) : 0;
+  const int sl_lo = half ? p.nslA : 0, nslh = pair ? (half ? p.nsl - p.nslA : p.nslA) : p.nsl;
   const int c_lo = 2 * sl_lo, nch = 2 * nslh;
   const int G = (nslh + p.nslg - 1) / p.nslg;                     // pooled groups of this CTA (fwd; bwd plans one group)
   int nmine = 0;
@@ -225,9 +234,9 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         const int b = cta + i * ncta;
         const int zb = p.w_batched ? b : 0;
         for (int c = c_lo; c < c_lo + nch; ++c) {
-          const long long t0 = p.trace ? clock64() : 0;
+          const long long t0 = trace ? clock64() : 0;
           mbar_wait(lempty_bar(s), ph ^ 1u);
-          if (p.trace) t_wait += clock64() - t0;
+          if (trace) t_wait += clock64() - t0;
           const uint32_t bar = lfull_bar(s), dst = ring + (uint32_t)(s * p.lbytes);
           mbar_arrive_expect_tx(bar, tx);
           for (int r = 0; r < tile_rows; r += 256)                 // two tiles per instruction, a last odd one alone
@@ -246,7 +255,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           if (++s == p.nL) { s = 0; ph ^= 1u; }
         }
       }
-      if (p.trace && blockIdx.x == 0) { g_trace[120] = t_wait; g_trace[121] = clock64() - t_begin; }   // L producer: ring-full wait, total
+      if (trace && blockIdx.x == 0) { g_trace[120] = t_wait; g_trace[121] = clock64() - t_begin; }   // L producer: ring-full wait, total
     }
   } else if (warp == 3) {
     // ---- P producer: the tall bricks of sample after sample, slice after slice (the MMA warp's group order is slice
@@ -264,16 +273,16 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         // would miss everything as soon as the live set exceeds the capacity)
         for (int sl = sl_lo + nslh - 1; sl >= sl_lo; --sl)
           for (int kp = 0; kp < p.nkp; ++kp) {
-            const long long t0 = p.trace ? clock64() : 0;
+            const long long t0 = trace ? clock64() : 0;
             mbar_wait(pempty_bar(s), ph ^ 1u);
-            if (p.trace) t_wait += clock64() - t0;
+            if (trace) t_wait += clock64() - t0;
             const bool last = kp == p.nkp - 1 && p.last_rows < 128;
             mbar_arrive_expect_tx(pfull_bar(s), last ? last_bytes : (uint32_t)kPBytes);
             tma_load_4d_hint(pring + (uint32_t)s * kPBytes, last ? &tm_bl : &tm_b, pfull_bar(s), 0, kp * 128, 2 * sl, b, pol_first);
             if (++s == p.nP) { s = 0; ph ^= 1u; }
           }
       }
-      if (p.trace && blockIdx.x == 0) { g_trace[125] = t_wait; g_trace[126] = clock64() - t_begin; }   // P producer
+      if (trace && blockIdx.x == 0) { g_trace[125] = t_wait; g_trace[126] = clock64() - t_begin; }   // P producer
     }
   } else if (warp == 1) {
     // ---- L MMA issue: the whole warp walks the chunks (uniform control flow, descriptors in uniform registers), one
@@ -286,28 +295,29 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const int nst = nslh * p.nkp;                                // tall bricks per sample (of this CTA)
       int ls = 0;
       uint32_t lph = 0;
-      long long t_wait = 0, t_gate = 0, t_begin = clock64();
+      long long t_wait = 0, t_gate = 0, t_issue = 0, t_begin = clock64();
       for (int j = 0; j < nmine; ++j) {
         const uint32_t acc = tmem_base + (uint32_t)((j % p.nbuf) * p.bufcols);
         for (int c = 0; c < nch; ++c) {
           // order against the other stream: the logit buffer is free (its previous sample's epilogue has read it), and
           // chunk c runs at most `lead` chunks ahead of the matching share of the previous sample's bricks
-          const long long tg = p.trace ? clock64() : 0;
+          const long long tg = trace ? clock64() : 0;
           if (c == 0 && j >= p.nbuf) {
-            while (*e_done < j - p.nbuf + 1) {}
+            while (*e_done < j - p.nbuf + 1) __nanosleep(64);
             tc_fence_after();
           }
           if (j > 0) {
             const int need = (j - 1) * nst + (c > p.lead ? (c - p.lead) * nst / nch : 0);
-            while (*p_issued < need) {}
+            while (*p_issued < need) __nanosleep(32);
           }
-          if (p.trace) t_gate += clock64() - tg;
-          const long long t0 = p.trace ? clock64() : 0;
+          if (trace) t_gate += clock64() - tg;
+          const long long t0 = trace ? clock64() : 0;
           mbar_wait(lfull_bar(ls), lph);
-          if (p.trace) t_wait += clock64() - t0;
+          if (trace) t_wait += clock64() - t0;
+          const long long ti = trace ? clock64() : 0;
           const uint32_t st0 = ring + (uint32_t)(ls * p.lbytes);
           const uint64_t bd = dK + (uint64_t)((st0 + (uint32_t)p.qoff) >> 4);
-          if (leader && !p.nomma) {
+          if (leader && !nomma) {
             for (int t = 0; t < p.ntiles; ++t) {
               // full tiles at toff, the short tail tile at the start of the stage (the MMA reads 128 rows there: the
               // rows past the tail are the query chunk / first tile and only reach accumulator rows n >= N)
@@ -322,14 +332,15 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           }
           if (leader) umma_commit(lempty_bar(ls));
           __syncwarp();
+          if (trace) t_issue += clock64() - ti;
           if (++ls == p.nL) { ls = 0; lph ^= 1u; }
         }
         if (leader) umma_commit(tfull_bar(j % p.nbuf));
         __syncwarp();
         EP_TRACE(j, 2);                                            // L warp: logits of sample j issued
       }
-      if (p.trace && blockIdx.x == 0 && lane == 0) {               // L warp: load-starved wait, ordering wait, total
-        g_trace[122] = t_wait; g_trace[123] = t_gate; g_trace[124] = clock64() - t_begin;
+      if (trace && blockIdx.x == 0 && lane == 0) {               // L warp: load-starved wait, ordering wait, total
+        g_trace[122] = t_wait; g_trace[123] = t_gate; g_trace[124] = clock64() - t_begin; g_trace[112] = t_issue;
       }
     }
   } else if (warp == 2) {
@@ -344,32 +355,35 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const uint32_t pcolw = kBwd ? (uint32_t)p.Mp : 2u * (uint32_t)p.Mp;      // accumulator columns per slice
       int ps = 0, issued = 0;
       uint32_t pph = 0;
-      long long t_wait = 0, t_gate = 0, t_begin = clock64();
+      long long t_wait = 0, t_gate = 0, t_free = 0, t_issue = 0, t_begin = clock64();
       for (int i = 0; i < nmine; ++i) {
         EP_TRACE(i, 0);                                            // P warp: start waiting for the operand blocks
-        const long long tg = p.trace ? clock64() : 0;
+        const long long tg = trace ? clock64() : 0;
         mbar_wait(eready_bar, (uint32_t)(i & 1));                  // operand blocks of sample i are in shared memory
         tc_fence_after();
-        if (p.trace) t_gate += clock64() - tg;
+        if (trace) t_gate += clock64() - tg;
         EP_TRACE(i, 1);                                            // P warp: pooled phase starts
         for (int g = 0; g < (kBwd ? 1 : G); ++g) {
           const int gg = kBwd ? 2 * i : i * G + g;                 // bwd: one group per sample, always buffer 0
           if (!kBwd) {                                             // this buffer's previous group has been drained
+            const long long tf = trace ? clock64() : 0;
             mbar_wait(pfree_bar(gg & 1), (((uint32_t)(gg >> 1)) & 1u) ^ 1u);
             tc_fence_after();
+            if (trace) t_free += clock64() - tf;
           }
           const int gs = kBwd ? nslh : min(p.nslg, nslh - g * p.nslg);
           for (int slg = 0; slg < gs; ++slg) {
             const uint32_t pacc = tmem_base + (uint32_t)p.pcol0 + (kBwd ? 0u : (uint32_t)((gg & 1) * p.pbufcols)) + (uint32_t)slg * pcolw;
             for (int kp = 0; kp < p.nkp; ++kp) {
-              const long long t0 = p.trace ? clock64() : 0;
+              const long long t0 = trace ? clock64() : 0;
               mbar_wait(pfull_bar(ps), pph);
-              if (p.trace) t_wait += clock64() - t0;
+              if (trace) t_wait += clock64() - t0;
+              const long long ti = trace ? clock64() : 0;
               const bool last = kp == p.nkp - 1 && p.last_rows < 128;
               const int ks = last ? p.kl : 8;
               const uint64_t ad = (last ? dMN_last : dMN) + (uint64_t)((pring + (uint32_t)ps * kPBytes) >> 4);
               const uint64_t bd0 = dK + (uint64_t)((blk_base + (uint32_t)(2 * kp) * 2u * half_bytes) >> 4);
-              if (leader && !p.nomma) {
+              if (leader && !nomma) {
                 for (int k = 0; k < ks; ++k) {
                   const uint64_t bd = bd0 + (uint64_t)((k >> 2) * (2u * half_bytes >> 4)) + 2u * (k & 3);
                   if (kBwd) {
@@ -383,6 +397,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
               ++issued;
               if (leader) { umma_commit(pempty_bar(ps)); *p_issued = issued; }
               __syncwarp();
+              if (trace) t_issue += clock64() - ti;
               if (++ps == p.nP) { ps = 0; pph ^= 1u; }
             }
           }
@@ -391,8 +406,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         }
         EP_TRACE(i, 3);                                            // P warp: sample i pooled
       }
-      if (p.trace && blockIdx.x == 0 && lane == 0) {               // P warp: load-starved wait, operand-block wait, total
-        g_trace[117] = t_wait; g_trace[118] = t_gate; g_trace[119] = clock64() - t_begin;
+      if (trace && blockIdx.x == 0 && lane == 0) {               // P warp: load-starved wait, operand-block wait, total
+        g_trace[117] = t_wait; g_trace[118] = t_gate; g_trace[119] = clock64() - t_begin; g_trace[113] = t_free; g_trace[114] = t_issue;
       }
     }
   } else if (warp >= 4) {
@@ -426,23 +441,56 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + j0), rh);
         tmem_ld16(acc + (uint32_t)(slg * 2 * p.Mp + p.Mp + j0), rl);
         tmem_ld_wait();
+        float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const int m = j0 + q;                                    // warp-uniform
-          if (m < p.M) {
-            const float v = (__uint_as_float(rh[q]) + __uint_as_float(rl[q])) *
-                            __shfl_sync(0xffffffffu, m < 32 ? invl[0] : invl[1], m & 31);
-            if (p.round_out) {                                     // P as bf16 hi/lo rows (b, m, {hi, lo}, d)
-              const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-              const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-              // streaming stores (evict-first in L2): the outputs must not displace the tokens waiting for their second fetch
-              unsigned short* pr = reinterpret_cast<unsigned short*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d;
-              __stcs(pr, __bfloat16_as_ushort(hi));
-              __stcs(pr + p.D, __bfloat16_as_ushort(lo));
-            } else {
-              __stcs(p.out + ((size_t)b * p.M + m) * p.D + d, v);
+          v[q] = (__uint_as_float(rh[q]) + __uint_as_float(rl[q])) * __shfl_sync(0xffffffffu, m < 32 ? invl[0] : invl[1], m & 31);
+        }
+        if (p.round_out) {
+          // P as bf16 hi/lo rows (b, m, {hi, lo}, d).  A lane holds one channel of 16 queries; an 8 x 8 transpose of
+          // query pairs among the 8 lanes of a group (3 butterfly stages) leaves lane j with queries 2j, 2j + 1 of the
+          // group's 8 consecutive channels: 16-byte streaming stores instead of 2-byte ones
+          uint32_t hp[8], lp[8];
+#pragma unroll
+          for (int pr = 0; pr < 8; ++pr) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * pr], v[2 * pr + 1]);
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * pr] - hf.x, v[2 * pr + 1] - hf.y);
+            hp[pr] = *reinterpret_cast<const uint32_t*>(&h);
+            lp[pr] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+#pragma unroll
+          for (int st = 4; st >= 1; st >>= 1) {
+            const bool up = (lane & st) != 0;
+#pragma unroll
+            for (int pr = 0; pr < 8; ++pr) {
+              if (pr & st) continue;
+              const uint32_t sh = __shfl_xor_sync(0xffffffffu, up ? hp[pr] : hp[pr | st], st);
+              const uint32_t sl = __shfl_xor_sync(0xffffffffu, up ? lp[pr] : lp[pr | st], st);
+              if (up) { hp[pr] = sh; lp[pr] = sl; } else { hp[pr | st] = sh; lp[pr | st] = sl; }
             }
           }
+          // streaming stores (evict-first in L2): the outputs must not displace the tokens waiting for their second fetch
+          const int d8 = d - (lane & 7);                           // first of the group's 8 channels
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const int m = j0 + 2 * (lane & 7) + hq;
+            if (m < p.M) {
+              const uint32_t sel = hq ? 0x7632u : 0x5410u;
+              const uint4 oh = make_uint4(__byte_perm(hp[0], hp[1], sel), __byte_perm(hp[2], hp[3], sel),
+                                          __byte_perm(hp[4], hp[5], sel), __byte_perm(hp[6], hp[7], sel));
+              const uint4 ol = make_uint4(__byte_perm(lp[0], lp[1], sel), __byte_perm(lp[2], lp[3], sel),
+                                          __byte_perm(lp[4], lp[5], sel), __byte_perm(lp[6], lp[7], sel));
+              unsigned short* prow = reinterpret_cast<unsigned short*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + d8;
+              __stcs(reinterpret_cast<uint4*>(prow), oh);
+              __stcs(reinterpret_cast<uint4*>(prow + p.D), ol);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (j0 + q < p.M) __stcs(p.out + ((size_t)b * p.M + j0 + q) * p.D + d, v[q]);
         }
       }
       tc_fence_before();
@@ -464,19 +512,55 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]) + __uint_as_float(r2[q]);
       }
     };
-    auto store_hilo = [&](uint8_t* blk, int m, int tt, float e) {
-      const __nv_bfloat16 hi = __float2bfloat16_rn(e);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
-      *reinterpret_cast<__nv_bfloat16*>(blk + blk_off(m, tt)) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(blk + half_bytes + blk_off(m, tt)) = lo;
+    // 16 queries (j0 ..) of this lane's token n -> the bf16 hi / lo operand rows of its 64-token block.  Conversions
+    // are the packed kind (two values per instruction on the FMA pipe; the single-value F2F runs on the 16-lane XU
+    // pipe and was the epilogue's bottleneck together with the exp), rows m >= M are left alone (they stay zero)
+    auto store_rows = [&](int n0, int n, int j0, const float (&x)[16]) {
+      uint8_t* rowb = blk_gen + (size_t)(n0 >> 6) * 2u * half_bytes + (uint32_t)j0 * 128u + (uint32_t)(n & 7) * 2u;
+      const uint32_t c3 = ((uint32_t)n & 63u) >> 3;
+#pragma unroll
+      for (int q = 0; q < 16; q += 2) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[q], x[q + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[q] - __uint_as_float(hb << 16), x[q + 1] - __uint_as_float(hb & 0xffff0000u));
+        const uint32_t lb = *reinterpret_cast<const uint32_t*>(&l2);
+        const uint32_t off0 = (uint32_t)q * 128u + ((c3 ^ (uint32_t)(q & 7)) << 4);
+        const uint32_t off1 = (uint32_t)(q + 1) * 128u + ((c3 ^ (uint32_t)((q + 1) & 7)) << 4);
+        if (j0 + q < p.M) {                                        // warp-uniform
+          *reinterpret_cast<unsigned short*>(rowb + off0) = (unsigned short)hb;
+          *reinterpret_cast<unsigned short*>(rowb + half_bytes + off0) = (unsigned short)lb;
+        }
+        if (j0 + q + 1 < p.M) {
+          *reinterpret_cast<unsigned short*>(rowb + off1) = (unsigned short)(hb >> 16);
+          *reinterpret_cast<unsigned short*>(rowb + half_bytes + off1) = (unsigned short)(lb >> 16);
+        }
+      }
     };
 
-    for (int i = 0; i < nmine; ++i) {
+    // fwd runs one extra iteration: the drain of the last sample's last group
+    for (int i = 0; i < nmine + (kBwd ? 0 : 1); ++i) {
       const int b = cta + i * ncta;
+      if (i < nmine) {
       const int buf = i % p.nbuf;
       if (warp == 4) EP_TRACE(i, 8);                               // epilogue: sample i begins
       // bwd: lane l keeps the row statistics of queries l and 32 + l of this sample
       float st_mx[2] = {0.f, 0.f}, st_inv[2] = {0.f, 0.f}, st_dl[2] = {0.f, 0.f};
+      float cache[kCache][16];
+      // bwd: A = exp(S - max) / sum of one unit from the saved logits (straight-line, loads issued together)
+      auto load_probs = [&](int t, int j0, float (&a)[16]) {
+        const int n = t * 128 + wq * 32 + lane;
+        const bool valid = n < p.N;
+        const float* srow = p.S + ((size_t)b * p.M + j0) * p.N + min(n, p.N - 1);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a[q] = __ldcs(srow + (size_t)min(q, p.M - 1 - j0) * p.N);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int m = min(j0 + q, p.M - 1);                      // warp-uniform
+          const float mx = __shfl_sync(0xffffffffu, m >= 32 ? st_mx[1] : st_mx[0], m & 31);
+          const float inv = __shfl_sync(0xffffffffu, m >= 32 ? st_inv[1] : st_inv[0], m & 31);
+          a[q] = valid ? ex2_ftz((a[q] - mx) * kLog2e) * inv : 0.f;
+        }
+      };
       if (kBwd) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -488,21 +572,30 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             st_dl[h] = __ldg(p.delta + bm);
           }
         }
+        if (!noepi) {
+          // the probabilities of this warp's first kCache units, recomputed from the saved logits while the dA MMAs
+          // of the sample still run (the loads do not depend on them)
+#pragma unroll
+          for (int k = 0; k < kCache; ++k) {
+            const int u = es + kSub * k;
+            const int t = u / upt, j0 = (u - t * upt) << 4;
+            if (u < nunits && t * 128 + wq * 32 < p.N) load_probs(t, j0, cache[k]);
+          }
+        }
       }
       mbar_wait(tfull_bar(buf), ((uint32_t)(i / p.nbuf)) & 1u);
       tc_fence_after();
       if (warp == 4) EP_TRACE(i, 9);                               // epilogue: logits complete
       const uint32_t acc = tmem_base + lane_base + (uint32_t)(buf * p.bufcols);
-      float cache[kCache][16];
       // pair mode: publish this CTA's partial logits (its half of D), then wait for the partner's; from here on
       // fetch_unit() returns the sum.  Scratch slot i & 1: the partner read slot i & 1 of sample i - 2 before it
       // published sample i - 1, which this CTA has already consumed.
       const float* peer = nullptr;
-      if (p.pair && !p.noepi) {
+      if (pair && !noepi) {
         const size_t slot_floats = (size_t)p.ntiles * p.Mp * 128;
         float* mine = p.xchg + ((size_t)blockIdx.x * 2 + (i & 1)) * slot_floats;
         peer = p.xchg + ((size_t)(blockIdx.x ^ 1) * 2 + (i & 1)) * slot_floats;
-        for (int u = es, k = 0; u < nunits; u += kSub, ++k) {
+        for (int u = es; u < nunits; u += kSub) {
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
@@ -523,50 +616,11 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       }
       auto fetch_unit = [&](int t, int j0, float (&v)[16]) {
         load_unit(acc, t, j0, v);
-        if (peer) {
+        if (pair && peer) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] += __ldcg(peer + ((size_t)t * p.Mp + j0 + q) * 128 + wq * 32 + lane);
         }
       };
-
-      if (!kBwd && !p.noepi) {
-        // ---- pass 1: per-query maximum over the tokens (per-warp partial rows, combined in a fixed order); the
-        // first kCache units of a warp stay in registers for pass 2
-        if (has_lo) pmax[ew * SW + lane] = -INFINITY;
-        if (has_hi) pmax[ew * SW + 32 + lane] = -INFINITY;
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < kCache; ++k) {
-          const int u = es + kSub * k;
-          const int t = u / upt, j0 = (u - t * upt) << 4;
-          if (u < nunits && t * 128 + wq * 32 < p.N) {             // (warp-uniform) some lane of this warp holds a token
-            fetch_unit(t, j0, cache[k]);
-            float v[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? cache[k][q] : -INFINITY;
-            const float red = reduce16<true>(v, lane);
-            if ((lane & 1) == 0) {
-              float* slot = pmax + ew * SW + j0 + ridx;
-              *slot = fmaxf(*slot, red);
-            }
-            __syncwarp();
-          }
-        }
-        for (int u = es + kSub * kCache; u < nunits; u += kSub) {
-          const int t = u / upt, j0 = (u - t * upt) << 4;
-          if (t * 128 + wq * 32 >= p.N) continue;
-          float v[16];
-          fetch_unit(t, j0, v);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? v[q] : -INFINITY;
-          const float red = reduce16<true>(v, lane);
-          if ((lane & 1) == 0) {
-            float* slot = pmax + ew * SW + j0 + ridx;
-            *slot = fmaxf(*slot, red);
-          }
-          __syncwarp();
-        }
-      }
       // the operand blocks may be rewritten once every pooled MMA of sample i - 1 has completed
       auto wait_blocks_free = [&]() {
         if (i > 0) {
@@ -576,8 +630,9 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           if (warp == 4) EP_TRACE(i, 10);                          // epilogue: pooled MMAs of sample i - 1 complete
         }
       };
-      if (kBwd || p.noepi) wait_blocks_free();
-      if (p.noepi) {
+
+      if (noepi) {
+        wait_blocks_free();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(eready_bar);
@@ -588,6 +643,39 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           for (int g = 0; g + 1 < G; ++g) { const int gg = i * G + g; mbar_wait(pdone_bar(gg & 1), ((uint32_t)(gg >> 1)) & 1u); __syncwarp(); if (lane == 0) mbar_arrive(pfree_bar(gg & 1)); }
         }
       } else if (!kBwd) {
+        // ---- pass 1: per-query maximum over the tokens (per-warp partial rows, combined in a fixed order).  TMEM reads
+        // run at 64 B / clock per SM, so the first kCache units of a warp stay in registers for the later passes
+        if (has_lo) pmax[ew * SW + lane] = -INFINITY;
+        if (has_hi) pmax[ew * SW + 32 + lane] = -INFINITY;
+        __syncwarp();
+        auto unit_max = [&](int t, int j0, const float (&x)[16]) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = (t * 128 + wq * 32 + lane < p.N) ? x[q] : -INFINITY;
+          const float red = reduce16<true>(v, lane);
+          if ((lane & 1) == 0) {
+            float* slot = pmax + ew * SW + j0 + ridx;
+            *slot = fmaxf(*slot, red);
+          }
+          __syncwarp();
+        };
+#pragma unroll
+        for (int k = 0; k < kCache; ++k) {
+          const int u = es + kSub * k;
+          const int t = u / upt, j0 = (u - t * upt) << 4;
+          if (u < nunits && t * 128 + wq * 32 < p.N) {             // (warp-uniform) some lane of this warp holds a token
+            fetch_unit(t, j0, cache[k]);
+            unit_max(t, j0, cache[k]);
+          }
+        }
+        for (int u = es + kSub * kCache; u < nunits; u += kSub) {
+          const int t = u / upt, j0 = (u - t * upt) << 4;
+          if (t * 128 + wq * 32 >= p.N) continue;
+          float v[16];
+          fetch_unit(t, j0, v);
+          unit_max(t, j0, v);
+        }
+        if (warp == 4) EP_TRACE(i, 4);                             // epilogue: pass 1 done
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
         float mx_lo = -INFINITY, mx_hi = -INFINITY;                // lane l: queries l and 32 + l
 #pragma unroll
@@ -598,24 +686,23 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (has_lo) psum[ew * SW + lane] = 0.f;
         if (has_hi) psum[ew * SW + 32 + lane] = 0.f;
         __syncwarp();
-        // ---- pass 2a (cached units; overlaps the tail of the previous sample's pooled phase): exp, row sums, saved
-        // logits -- the probabilities replace the logits in the register cache
-        auto emit = [&](int t, int j0, float (&v)[16], bool to_blocks) {
-          const int n = t * 128 + wq * 32 + lane;
+        wait_blocks_free();
+        // ---- pass 2: exp, row sums and the operand blocks of the pooled phase: what the P warp waits for.  Straight-line
+        // code, the 16 queries of a unit are independent chains
+        auto unit_exp = [&](int t, int j0, const float (&x)[16]) {
+          const int n0 = t * 128 + wq * 32;                        // warp-uniform; its 32 tokens lie in one 64-token block
+          const int n = n0 + lane;
           const bool valid = n < p.N;
-          const int kb = n >> 6, tt = n & 63;
-          uint8_t* blk = (to_blocks && kb < p.nkb) ? blk_gen + (size_t)kb * 2u * half_bytes : nullptr;
-          float* srow = p.S + ((size_t)b * p.M + j0) * p.N + n;
+          float e[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const int m = j0 + q;                                  // warp-uniform
-            const float mx = __shfl_sync(0xffffffffu, m < 32 ? mx_lo : mx_hi, m & 31);
-            const bool on = valid && m < p.M;
-            if (on && half == 0) __stcs(srow + (size_t)q * p.N, v[q]);
-            v[q] = on ? __expf(v[q] - mx) : 0.f;
-            if (blk && m < p.M) store_hilo(blk, m, tt, v[q]);
+            const float mxs = __shfl_sync(0xffffffffu, m < 32 ? mx_lo : mx_hi, m & 31) * kLog2e;
+            const float ex = ex2_ftz(fmaf(x[q], kLog2e, -mxs));
+            e[q] = (valid && m < p.M) ? ex : 0.f;
           }
-          const float red = reduce16<false>(v, lane);
+          store_rows(n0, n, j0, e);
+          const float red = reduce16<false>(e, lane);
           if ((lane & 1) == 0) psum[ew * SW + j0 + ridx] += red;
           __syncwarp();
         };
@@ -623,31 +710,14 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         for (int k = 0; k < kCache; ++k) {
           const int u = es + kSub * k;
           const int t = u / upt, j0 = (u - t * upt) << 4;
-          if (u < nunits && t * 128 + wq * 32 < p.N) emit(t, j0, cache[k], false);
-        }
-        // ---- pass 2b: the operand blocks, once the previous sample's pooled MMAs have stopped reading them
-        wait_blocks_free();
-#pragma unroll
-        for (int k = 0; k < kCache; ++k) {
-          const int u = es + kSub * k;
-          const int t = u / upt, j0 = (u - t * upt) << 4;
-          if (u < nunits && t * 128 + wq * 32 < p.N) {
-            const int n = t * 128 + wq * 32 + lane;
-            const int kb = n >> 6, tt = n & 63;
-            if (kb < p.nkb) {
-              uint8_t* blk = blk_gen + (size_t)kb * 2u * half_bytes;
-#pragma unroll
-              for (int q = 0; q < 16; ++q)
-                if (j0 + q < p.M) store_hilo(blk, j0 + q, tt, cache[k][q]);
-            }
-          }
+          if (u < nunits && t * 128 + wq * 32 < p.N) unit_exp(t, j0, cache[k]);
         }
         for (int u = es + kSub * kCache; u < nunits; u += kSub) {
           const int t = u / upt, j0 = (u - t * upt) << 4;
           if (t * 128 + wq * 32 >= p.N) continue;
           float v[16];
           fetch_unit(t, j0, v);
-          emit(t, j0, v, true);
+          unit_exp(t, j0, v);
         }
         fence_proxy_async();                                       // generic-proxy block writes -> visible to the MMAs
         tc_fence_before();
@@ -655,14 +725,12 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (lane == 0) mbar_arrive(eready_bar);
         if (warp == 4) EP_TRACE(i, 12);                            // epilogue: operand blocks written
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
-        if (ew == 0 && lane == 0) *e_done = i + 1;                 // every warp has read the logit accumulators of sample i
         // row sums of this sample (for its drains) and the saved statistics
         if (ew == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int m = 32 * h + lane;
             float su = 0.f;
-#pragma unroll
             if (m < SW)
               for (int w = 0; w < kEW; ++w) su += psum[w * SW + m];
             tot[(i & 1) * 64 + m] = su;
@@ -673,40 +741,64 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
-        // drains: the last group of the previous sample, then this sample's groups but the last (which completes
-        // together with the next sample's logits)
-        if (i > 0) drain_group(b - ncta, i - 1, G - 1);
-        for (int g = 0; g + 1 < G; ++g) drain_group(b, i, g);
-        if (warp == 4) EP_TRACE(i, 13);                            // epilogue: drains done
-      } else {
-        // ---- backward: dS = A (dA - delta), A recomputed from the saved logits and row statistics
-        for (int u = es; u < nunits; u += kSub) {
-          const int t = u / upt, j0 = (u - t * upt) << 4;
-          if (t * 128 + wq * 32 >= p.N) continue;
-          const int n = t * 128 + wq * 32 + lane;
-          const bool valid = n < p.N;
-          float sv[16];
+        // ---- pass 3, off the critical path (the pooled MMAs of the sample are running): the saved logits.  Their
+        // stores are what the load/store unit is slowest at (rows of N floats are not 16-byte aligned in general), so
+        // the upper half of each quadrant's warps writes them, re-reading TMEM, while the lower half starts draining;
+        // the logit accumulators of the sample are released when they are through
+        if (es >= kSub / 2) {
+          if (half == 0) {
+            for (int u = es - kSub / 2; u < nunits; u += kSub / 2) {
+              const int t = u / upt, j0 = (u - t * upt) << 4;
+              if (t * 128 + wq * 32 >= p.N) continue;
+              float v[16];
+              fetch_unit(t, j0, v);
+              const int n = t * 128 + wq * 32 + lane;
+              if (n < p.N) {
+                float* srow = p.S + ((size_t)b * p.M + j0) * p.N + n;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {                           // issued before the TMEM wait: independent loads
-            const int m = min(j0 + q, p.M - 1);
-            sv[q] = valid ? __ldcs(p.S + ((size_t)b * p.M + m) * p.N + n) : 0.f;
-          }
-          float v[16];
-          fetch_unit(t, j0, v);
-          const int kb = n >> 6, tt = n & 63;
-          uint8_t* blk = kb < p.nkb ? blk_gen + (size_t)kb * 2u * half_bytes : nullptr;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int m = j0 + q;                                  // warp-uniform
-            if (m < p.M) {
-              const bool h = m >= 32;
-              const float mx = __shfl_sync(0xffffffffu, h ? st_mx[1] : st_mx[0], m & 31);
-              const float inv = __shfl_sync(0xffffffffu, h ? st_inv[1] : st_inv[0], m & 31);
-              const float dl = __shfl_sync(0xffffffffu, h ? st_dl[1] : st_dl[0], m & 31);
-              const float ds = valid ? __expf(sv[q] - mx) * inv * (v[q] - dl) : 0.f;
-              if (blk) store_hilo(blk, m, tt, ds);
+                for (int q = 0; q < 16; ++q)
+                  if (j0 + q < p.M) __stcs(srow + (size_t)q * p.N, v[q]);
+              }
             }
           }
+          tc_fence_before();
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * kEW / 2) : "memory");
+          if (ew == kEW / 2 && lane == 0) *e_done = i + 1;         // the logit accumulators of sample i are free
+        }
+      } else {
+        // ---- backward: dS = A (dA - delta), A recomputed from the saved logits and row statistics
+        wait_blocks_free();
+        // dS of one unit -> operand blocks (straight-line: independent chains per query)
+        auto emit_ds = [&](int t, int j0, const float (&a)[16], const float (&v)[16]) {
+          const int n0 = t * 128 + wq * 32;                        // warp-uniform; its 32 tokens lie in one 64-token block
+          const int n = n0 + lane;
+          float ds[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int m = min(j0 + q, p.M - 1);                    // warp-uniform
+            const float dl = __shfl_sync(0xffffffffu, m >= 32 ? st_dl[1] : st_dl[0], m & 31);
+            ds[q] = n < p.N ? a[q] * (v[q] - dl) : 0.f;
+          }
+          store_rows(n0, n, j0, ds);
+        };
+#pragma unroll
+        for (int k = 0; k < kCache; ++k) {                         // units whose A is already in registers
+          const int u = es + kSub * k;
+          const int t = u / upt, j0 = (u - t * upt) << 4;
+          if (u < nunits && t * 128 + wq * 32 < p.N) {
+            float v[16];
+            fetch_unit(t, j0, v);
+            emit_ds(t, j0, cache[k], v);
+          }
+        }
+        for (int u = es + kSub * kCache; u < nunits; u += kSub) {
+          const int t = u / upt, j0 = (u - t * upt) << 4;
+          if (t * 128 + wq * 32 >= p.N) continue;
+          float a[16];
+          load_probs(t, j0, a);
+          float v[16];
+          fetch_unit(t, j0, v);
+          emit_ds(t, j0, a, v);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -716,10 +808,17 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
         if (ew == 0 && lane == 0) *e_done = i + 1;                 // every warp has read the dA accumulators of sample i
       }
+      }  // i < nmine
+      if (!kBwd && !noepi) {
+        // drains: the last group of the previous sample, then this sample's groups but the last (which completes
+        // together with the next sample's logits)
+        const int g_hi = i < nmine ? G - 1 : 0;
+        for (int dg = i > 0 ? -1 : 0; dg < g_hi; ++dg)
+          drain_group(dg < 0 ? b - ncta : b, dg < 0 ? i - 1 : i, dg < 0 ? G - 1 : dg);
+        if (warp == 4 && i < nmine) EP_TRACE(i, 13);               // epilogue: drains done
+      }
     }
-    if (nmine > 0 && !kBwd) {
-      drain_group(cta + (nmine - 1) * ncta, nmine - 1, G - 1);
-    } else if (nmine > 0) {
+    if (nmine > 0 && kBwd) {
       // bwd: the query-gradient partial of this CTA, all slices
       const int gl = 2 * (nmine - 1);
       mbar_wait(pdone_bar(0), ((uint32_t)(gl >> 1)) & 1u);
@@ -884,8 +983,13 @@ int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int 
   p.last_rows = pl.last_rows; p.pair = pl.pair; p.nslA = pl.nslA;
   p.trace = (g_debug & 2048) ? 1 : 0; p.nomma = (g_debug & 4096) ? 1 : 0; p.noepi = (g_debug & 8192) ? 1 : 0;
   p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff; p.toff = pl.toff;
-  if ((rc = set_smem(fused_kernel<kBwd>, pl.smem))) return rc;
-  fused_kernel<kBwd><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
+  if (p.trace || p.nomma || p.noepi || p.pair) {                  // developer knobs: the instrumented instantiation
+    if ((rc = set_smem(fused_kernel<kBwd, true>, pl.smem))) return rc;
+    fused_kernel<kBwd, true><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
+  } else {
+    if ((rc = set_smem(fused_kernel<kBwd, false>, pl.smem))) return rc;
+    fused_kernel<kBwd, false><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
+  }
   EP_LAUNCH_CHECK();
   return 0;
 }

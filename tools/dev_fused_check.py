@@ -97,6 +97,7 @@ def trace(B, N, D, M, bwd=False, flags=0):
     tr.train_step(x, y)
     torch.cuda.synchronize()
     lib.ep_set_debug(2048 | flags)
+    lib.ep_set_sm_limit(int(os.environ.get("EP_SM_LIMIT", "0")))
     if bwd:
         tr._cx, tr._ct = x, y
         tr._part2()
@@ -105,11 +106,12 @@ def trace(B, N, D, M, bwd=False, flags=0):
         tr._forward(True)
     torch.cuda.synchronize()
     lib.ep_set_debug(0)
+    lib.ep_set_sm_limit(0)
     buf = (ctypes.c_longlong * 128)()
     lib.ep_debug_trace(ctypes.cast(buf, ctypes.c_void_p), 128)
     t = [buf[i] for i in range(128)]
     t0 = min(v for v in t[:112] if v > 0)
-    names = {0: "P:wait_blocks", 1: "P:start", 3: "P:issued", 2: "L:issued", 8: "epi:begin", 9: "epi:logits_ready",
+    names = {0: "P:wait_blocks", 1: "P:start", 3: "P:issued", 2: "L:issued", 4: "epi:pass1", 5: "u0:pre", 6: "u0:loaded", 7: "u0:stored", 11: "u0:summed", 8: "epi:begin", 9: "epi:logits_ready",
              10: "epi:P_prev_done", 12: "epi:blocks_written", 13: "epi:drains_done"}
     print(f"trace {'bwd' if bwd else 'fwd'} B{B} N{N} D{D} M{M}")
     for i in range(2, 5):
@@ -118,6 +120,7 @@ def trace(B, N, D, M, bwd=False, flags=0):
     print(f"  L producer: ring-full wait {t[120] / 1965.0:.1f} us of {t[121] / 1965.0:.1f};  P producer: {t[125] / 1965.0:.1f} of {t[126] / 1965.0:.1f};  "
           f"L warp: load wait {t[122] / 1965.0:.1f} us, order wait {t[123] / 1965.0:.1f} us of {t[124] / 1965.0:.1f};  "
           f"P warp: load wait {t[117] / 1965.0:.1f} us, block wait {t[118] / 1965.0:.1f} us of {t[119] / 1965.0:.1f}")
+    print(f"  L warp issue {t[112] / 1965.0:.1f} us;  P warp: drain (pfree) wait {t[113] / 1965.0:.1f} us, issue {t[114] / 1965.0:.1f} us")
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweep":
@@ -128,8 +131,4 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweep":
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "trace":
     trace(1024, 257, 1024, 32)
-    trace(1024, 257, 1024, 32, flags=4096)
-    trace(1024, 257, 1024, 32, flags=8192)
-    trace(1024, 257, 1024, 32, flags=8192 | 4096)
     trace(1024, 257, 1024, 32, bwd=True)
-    trace(1024, 257, 1024, 8)
