@@ -11,15 +11,19 @@ batch that is already resident in HBM; batches cycle through a pool of `--pool` 
 (8 x 539 MB >> 126 MB L2, so every step streams its tokens from HBM).  Weak scaling: per-GPU batch fixed.
 
 One JSON line on stdout (rank 0).  Extra keys next to the contract's:
-  roofline      the slowest of the four token-streaming kernels (ks<0> logits, kp<0> pool, ks<1> dS,
-                kp<1> dq), each timed with CUDA events on its launching stream; achieved = B*N*D*2 bytes
-                (algorithmic: each bf16 token read once per kernel, SURVEY.md 8d) / duration;
-                peak = MEASURED_PEAKS.json hbm_gbs.  roofline_all_streaming_kernels lists all four.
+  roofline      the slower of the token-streaming kernels (the one-pass "fused fwd" / "fused bwd" where the
+                shape allows them, else ks<2> logits+softmax, kp<0> pool, ks<1> dS, kp<1> dq), each timed
+                with CUDA events on its launching stream; achieved = B*N*D*2 bytes (algorithmic: each bf16
+                token crosses HBM once per direction) / duration; peak = MEASURED_PEAKS.json
+                hbm_gbs.  roofline_all_streaming_kernels lists all of them; `traffic` is the kernel's
+                measured DRAM bytes (ncu, profiles/traffic.json).
   step_roofline_frac   (2*B*N*D*2 bytes / step time) / peak -- the whole step against the roofline.
   cpu_baseline  the oracle (CPU restatement of the reference head, torch fp32, all host threads) on a
                 bounded sample of the same workload.
   e2e           the same step through EPHeadTrainer.train_step_host: pinned-host tokens and labels copied
-                H2D and the loss read back D2H inside the timed region, every step.
+                H2D and the loss read back D2H inside the timed region, every step; h2d_gbs_per_gpu is
+                the copy rate each GPU saw.  Each rank pins itself to its GPU's NUMA-local cores first
+                (NVML's ideal CPU affinity) so that the pinned staging buffers are allocated there.
 """
 import argparse
 import json
@@ -51,6 +55,21 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def pin_to_gpu_numa(index):
+    """Bind this process to the CPUs NVML reports as local to GPU `index`; returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus {cpus[0]}-{cpus[-1]}"
+    except Exception as e:                                        # a report, never a gate
+        return f"unchanged ({type(e).__name__})"
 
 
 class ClockSampler:
@@ -210,6 +229,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: efficient_probing_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa(local)                            # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the gradient all-reduce overlaps the token-streaming backward kernels, which leave `comm_sms` SMs free
@@ -358,7 +378,8 @@ def main():
                     "replica_max_abs_diff": replica_diff},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(ms2) / e2e_steps},
+                    "ms_per_step": float(ms2) / e2e_steps,
+                    "h2d_gbs_per_gpu": h2d / (float(ms2) / e2e_steps * 1e-3) / 1e9, "cpu_affinity": affinity},
             "gpu_launches": (tr.launches_per_step or 0) * args.steps,
             "launches_per_step": tr.launches_per_step,
             "roofline": r_dom, "roofline_all_streaming_kernels": per_kernel,

@@ -1,7 +1,12 @@
+#!/bin/bash
+# Round-2 single-GPU evidence: bench lines of every config, the reference arm, the ncu launch list of a step, a full
+# ncu capture of the one-pass kernels and a memcheck run.  Writes into gpurun_out/ (copied to profiles/ by hand).
 set -x
-timeout 300 python -m pytest tests/test_parity_gpu.py -x -q -k "saved_pooled or fused_and" 2>&1 | tail -2
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-for c in c3 c4 c5; do timeout 400 python bench.py --config $c --no-cpu-baseline --steps 20 > gpurun_out/bench_${c}_M32.json 2>/dev/null; tail -c 200 gpurun_out/bench_${c}_M32.json | head -c 60; echo; done
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json 2>/dev/null; head -c 300 gpurun_out/bench_reference_arm.json; echo
-timeout 300 python bench.py --kernel-mode 1 --no-cpu-baseline --steps 5 > gpurun_out/bench_v0_general_kernels.json 2>/dev/null
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'ks_kernel<1>|kp_kernel<1>' -c 4 -o gpurun_out/streaming_bwd -f python tools/stage_times.py --only ep_fwd,bwd_proj,bwd_pool --iters 1 > gpurun_out/ncu_full_bwd.log 2>&1; tail -2 gpurun_out/ncu_full_bwd.log
+timeout 600 python bench.py > gpurun_out/r02_bench_c2_M32.json 2> gpurun_out/bench_c2.err; tail -c 300 gpurun_out/r02_bench_c2_M32.json | head -c 120; echo
+timeout 300 python bench.py --steps 200 --no-cpu-baseline > gpurun_out/r02_bench_c2_M32_200steps.json 2>/dev/null
+timeout 300 python bench.py --queries 8 --no-cpu-baseline > gpurun_out/r02_bench_c2_M8.json 2>/dev/null
+bash tools/bench_multi.sh 1 "c3 c4 c5"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2>/dev/null; head -c 300 gpurun_out/r02_bench_reference_arm.json; echo
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launch_list.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_ll.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 2 -o gpurun_out/r02_fused_full -f python tools/profile_step.py c2 32 3 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
+timeout 600 compute-sanitizer --tool memcheck python tools/dev_memcheck_step.py > gpurun_out/r02_compute_sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/r02_compute_sanitizer_memcheck.log
