@@ -221,15 +221,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tmem_ld_wait();
           const int col = j0 + c0;
           if (row < g.I && col + 16 <= g.J) {
-            __align__(32) __nv_bfloat16 hi[16], lo[16];
+            // packed conversions (two values per instruction on the FMA pipe; the single-value F2F shares the
+            // 16-lane XU pipe)
+            __align__(32) uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float v = __uint_as_float(r[i]);
-              hi[i] = __float2bfloat16_rn(v);
-              lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
+            for (int i = 0; i < 8; ++i) {
+              const float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+              hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xffff0000u));
+              lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
             }
-            st_global_256(hrow + col, reinterpret_cast<const uint32_t*>(hi));          // one full 32-byte sector
-            st_global_256(hrow + g.J + col, reinterpret_cast<const uint32_t*>(lo));    // per lane and store
+            st_global_256(hrow + col, hi);                                             // one full 32-byte sector
+            st_global_256(hrow + g.J + col, lo);                                       // per lane and store
           }
         }
       } else {

@@ -511,6 +511,45 @@ kp_kernel(const __grid_constant__ CUtensorMap tm_x, const KPParams p) {
         uint32_t r[16];
         tmem_ld16(acc + (uint32_t)(sl * p.J + j0), r);
         tmem_ld_wait();
+        if (kMode == 0 && p.round_out) {
+          // P as bf16 hi/lo rows (b, m, {hi, lo}, d): same bytes as fp32.  A lane holds one channel of 8 queries; an
+          // 8 x 8 transpose among the 8 lanes of a group (hi | lo packed per query, 3 butterfly stages) leaves lane j
+          // with query j of the group's 8 consecutive channels: two 16-byte stores instead of sixteen 2-byte ones
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const int m0 = (j0 >> 1) + i;                    // warp-uniform
+            const float v0 = (__uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1])) * __shfl_sync(0xffffffffu, invl[(m0 >> 5) & 1], m0 & 31);
+            const float v1 = (__uint_as_float(r[2 * i + 2]) + __uint_as_float(r[2 * i + 3])) * __shfl_sync(0xffffffffu, invl[((m0 + 1) >> 5) & 1], (m0 + 1) & 31);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
+            const uint32_t lb = *reinterpret_cast<const uint32_t*>(&l2);
+            w[i] = __byte_perm(hb, lb, 0x5410);              // (hi, lo) of query i
+            w[i + 1] = __byte_perm(hb, lb, 0x7632);
+          }
+#pragma unroll
+          for (int st = 4; st >= 1; st >>= 1) {
+            const bool up = (lane & st) != 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q & st) continue;
+              const uint32_t got = __shfl_xor_sync(0xffffffffu, up ? w[q] : w[q | st], st);
+              if (up) w[q] = got; else w[q | st] = got;
+            }
+          }
+          const int m = (j0 >> 1) + (lane & 7);
+          if (m < p.M) {
+            const uint4 oh = make_uint4(__byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410),
+                                        __byte_perm(w[4], w[5], 0x5410), __byte_perm(w[6], w[7], 0x5410));
+            const uint4 ol = make_uint4(__byte_perm(w[0], w[1], 0x7632), __byte_perm(w[2], w[3], 0x7632),
+                                        __byte_perm(w[4], w[5], 0x7632), __byte_perm(w[6], w[7], 0x7632));
+            unsigned short* pr = reinterpret_cast<unsigned short*>(p.out) + (((size_t)b * p.M + m) * 2) * p.D + (d - (lane & 7));
+            *reinterpret_cast<uint4*>(pr) = oh;
+            *reinterpret_cast<uint4*>(pr + p.D) = ol;
+          }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int m = (j0 >> 1) + i;                       // warp-uniform
