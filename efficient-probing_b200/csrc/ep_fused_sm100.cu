@@ -18,13 +18,14 @@
 // that L(i+1) advances in step with P(i), which bounds the L2 footprint to one sample plus the lead per CTA).  That
 // needs the logit accumulators double-buffered, which decides the operand layouts:
 // fp32 operands (queries, probabilities, dP, dS) are bf16 hi/lo pairs as in ep_pool_sm100.cu; in the logit phase the
-// pair is two K-steps into ONE accumulator column (hi rows and lo rows are separate B operands): 2 x 96 columns at
-// N = 257, M = 32.  Forward pooled phase: hi and lo are separate columns of one N = 2 Mp MMA, D is walked in groups
-// of slices whose accumulators ping-pong between two TMEM buffers (2 x 2 slices x 64 columns), so a group drains
-// while the next accumulates.  Backward: the query gradient accumulates over the whole launch, all of D resident
-// (8 slices x 32 columns, hi/lo as two K-steps).  A tcgen05.mma with N <= 64 occupies the tensor core for 40-48
-// cycles whatever N (tools/dev_umma_probe.cu: 39/40/48/64/128 cycles at N = 16/32/64/128/256), so the MMA warp issues
-// from uniform registers with the whole warp converged.
+// pair is either two columns of one N = 2 Mp MMA (added when leaving TMEM) or two K-steps into ONE column (hi rows
+// and lo rows as separate B operands, twice the MMAs), whichever lets TMEM hold two logit buffers next to the pooled
+// accumulators (make_fplan; c2 forward: 2 x 3 tiles x 64 columns + 2 x 64).  Forward pooled phase: hi and lo are
+// separate columns of one N = 2 Mp MMA, D is walked in groups of slices whose accumulators ping-pong between two
+// TMEM buffers, so a group drains while the next accumulates.  Backward: the query gradient accumulates over the
+// whole launch, all of D resident (8 slices x 32 columns, hi/lo as two K-steps).  A tcgen05.mma with N <= 64
+// occupies the tensor core for 40-48 cycles whatever N (tools/dev_umma_probe.cu: 39/40/48/64/128 cycles at
+// N = 16/32/64/128/256), so the MMA warp issues from uniform registers with the whole warp converged.
 //
 // Pipeline bookkeeping is sized by what the primitives cost when issued from one thread (tools/dev_issue_probe.cu, SM
 // cycles): a TMA load 120-170, mbarrier.try_wait on a completed phase 170, tcgen05.commit 45.  With a barrier pair per
@@ -38,11 +39,24 @@
 // `lead` chunks) and the epilogue has released the logit buffer.  The L producer also prefetches into L2 a few chunks
 // ahead (cp.async.bulk.prefetch.tensor), so that the two chunk stages shared memory has room for cover L2 latency.
 //
-// What was measured (profiles/r02_*): with 148 CTAs the live tokens (148 x (one sample + lead) = 80-100 MB at c2) do
-// NOT survive in L2 between their two fetches -- dram__bytes_read is 1.0 GB per pass at c2, twice the tokens; it is
-// 0.55 GB with 74 CTAs.  About half of the 126 MB is usable for this pattern, so at c2 / c3 the second fetch is an
-// HBM read again and the kernel runs at the speed of the two kernels it replaces (it still saves their operand
-// blocks and launches).  Shapes whose 148 samples fit (N x D x 2 B <= ~390 KB) get the single HBM read.
+// What was measured (profiles/r02_*, DESIGN.md sections 5-6):
+//  * L2.  With 148 CTAs the live tokens (148 x (one sample + lead) = 80-100 MB at c2) only partly survive in L2
+//    between their two fetches: dram__bytes_read is 0.78 GB (forward) / 0.94 GB (backward, incl. 0.13 GB of dP) per
+//    pass at c2 against 0.54 GB of tokens; the miss rate falls gradually with fewer CTAs (0.68 GB at 104, 0.55 GB at
+//    74) but every CTA taken away costs more than its misses, so all SMs are used.
+//  * tcgen05.mma issue is effectively synchronous for the issuing thread (tools/dev_mix_probe.cu: 48 cycles per
+//    N = 64 MMA whether one warp issues or two interleave, and any extra latency in the issuing loop shows up in
+//    full), so every barrier round trip of an MMA warp idles the tensor core unless the other MMA warp is issuing.
+//  * The epilogue is bound by three narrow pipes (tools/dev_epi_probe.cu, cycles per 16-query unit with 16 warps):
+//    the 16-lane XU pipe shared by ex2 and single-value F2F conversions (exp 540, + hi/lo split with F2F 1580, with
+//    packed F2FP 835), the load/store unit on the saved logits (rows of N floats, 4-byte aligned only: 1440), and TMEM
+//    reads (64 B / clock).  Hence: packed conversions, 16-byte pooled-token stores through a register transpose, the
+//    logits of a warp's first units kept in registers between the softmax passes, and the saved logits written after
+//    the pooled phase has been released (by the warps that have no drain work).
+//  * Code size: the kernel is executed phase by phase by 20 warps in five roles; with every developer knob compiled
+//    in it was 145 KB of SASS and its instruction-cache misses cost ~10 % -- the knobs now live in a separate
+//    instantiation (kDev) and each epilogue phase exists once (62 KB forward, 90 KB backward).
+//  c2, M = 32: forward 249 -> 213 us, backward 227 -> 192 us (the two kernels each replaces: 243 / 251 us).
 //
 // Pair mode (developer knob, ep_set_debug bit 29).  CTAs 2k and 2k+1 share sample k, 74 + k, ...: each takes half of
 // the d-slices in BOTH phases (half the chunks, half the bricks), the partial logits are exchanged through a global

@@ -18,6 +18,8 @@ four become ready before the token-streaming half of the backward (ep_bwd_pool),
 issued on a communication stream underneath it; cls_token's 0.1-0.5 MB follows."""
 from typing import Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -330,7 +332,8 @@ class EPHeadTrainer:
             # single GPU: the whole step is one graph.  Multi-GPU: the NCCL all-reduces stay outside the
             # graphs (three graphs per step with the two exchanges between them) -- capturing the
             # collectives inside a graph deadlocked on this stack, and the eager calls cost microseconds.
-            parts = [self._step_body] if self.world == 1 else [self._part1, self._part2, self._part3]
+            one_graph = self.world == 1 or os.environ.get("EP_GRAPH_NCCL", "0") == "1"   # experimental: NCCL captured too
+            parts = [self._step_body] if one_graph else [self._part1, self._part2, self._part3]
             graphs = []
             for part in parts:
                 g = torch.cuda.CUDAGraph()
@@ -350,7 +353,7 @@ class EPHeadTrainer:
                 self._step_body()
             return
         graphs = self._ensure_graphs()
-        if self.world == 1:
+        if len(graphs) == 1:
             graphs[0].replay()
         else:
             graphs[0].replay()

@@ -69,7 +69,10 @@ int ep_last_kernel_family(void);
 /* Developer knob: bit 5 (32) makes ep_fwd / ep_bwd_proj / ep_bwd_pool bracket each of their kernels with
  * CUDA events on the call's stream (one host sync per call) and record the durations, read back with
  * ep_timing_*; bit 8 (256) also prints them; bit 9 (512) runs the forward softmax as a separate kernel instead
- * of in the logit kernel's epilogue (same results).  Other bits are ignored.  0 in normal use. */
+ * of in the logit kernel's epilogue (same results); bit 10 (1024) selects the two-kernel path per direction
+ * instead of the one-pass kernels (same results; cross-check).  Bits 11-13 and 16-29 select the instrumented
+ * instantiation of the one-pass kernels (pipeline stamps, timing experiments whose RESULTS ARE GARBAGE, plan
+ * overrides: csrc/ep_fused_sm100.cu).  0 in normal use. */
 int ep_set_debug(int flags);
 int ep_timing_count(void);
 int ep_timing_get(int i, char* name, int name_len, float* microseconds);
