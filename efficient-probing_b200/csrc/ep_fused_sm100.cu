@@ -96,6 +96,8 @@ struct FParams {
                                        // tile is a short box sharing its slot with the query chunk
   int nchunks, nkb, nsl, nL, nP, lbytes, lead, nbuf, bufcols, pcol0, tmem_cols, w_batched, qoff, toff;   // nL/nP ring stages; chunk stage = [tail tile @0][query chunk @qoff][token tiles @toff]
   int nkp, pf;                         // tall bricks per slice (= ceil(nkb / 2)); L2 prefetch distance in chunks
+  int nstream;                         // first chunks of a sample fetched evict_first: they are re-read last and would not
+                                       // survive in L2 anyway; keeping them out protects the rest (see make_fplan)
   int nslg, G, pbufcols;               // pooled phase: G groups of <= nslg slices, accumulator buffers of pbufcols columns
   int lsplit;                          // logit phase: 1 = hi/lo query rows as two K-steps into one column (N = Mp),
                                        //              0 = as separate columns of one N = 2 Mp MMA (added in the epilogue)
@@ -113,6 +115,7 @@ struct FParams {
   int trace;
   int noepi;                           // developer: epilogue warps only run the barrier protocol
   int nomma;                           // developer: skip the MMA instructions (timing experiments; results are garbage)
+  int skip;                            // developer: bit 0 skip the operand-block stores, bit 1 the row sums, bit 2 the exp (garbage results)
 };
 
 __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
@@ -239,7 +242,8 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     // qoff][nfull x 16 KB token tiles at toff]
     if (lane == 0 && nmine > 0) {
       const uint64_t pol_last = policy_evict_last();
-      const uint64_t pol_w = p.w_batched ? policy_evict_first() : pol_last;   // per-sample dP rows are read once
+      const uint64_t pol_stream = policy_evict_first();
+      const uint64_t pol_w = p.w_batched ? pol_stream : pol_last;           // per-sample dP rows are read once
       const uint32_t tx = w_bytes + (mixed_tail ? (uint32_t)p.tail_rows * 128u : 0u) + (uint32_t)p.nfull * kSlotBytes;
       int s = 0;
       uint32_t ph = 0;
@@ -253,11 +257,12 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           if (trace) t_wait += clock64() - t0;
           const uint32_t bar = lfull_bar(s), dst = ring + (uint32_t)(s * p.lbytes);
           mbar_arrive_expect_tx(bar, tx);
+          const uint64_t pol_x = (c - c_lo) < p.nstream ? pol_stream : pol_last;
           for (int r = 0; r < tile_rows; r += 256)                 // two tiles per instruction, a last odd one alone
-            tma_load_3d_hint(dst + (uint32_t)p.toff + (uint32_t)r * 128u, tile_rows - r >= 256 ? &tm_x : &tm_x1, bar, c * 64, r, b, pol_last);
+            tma_load_3d_hint(dst + (uint32_t)p.toff + (uint32_t)r * 128u, tile_rows - r >= 256 ? &tm_x : &tm_x1, bar, c * 64, r, b, pol_x);
           tma_load_4d_hint(dst + (uint32_t)p.qoff, &tm_w, bar, c * 64, 0, 0, zb, pol_w);
           tma_load_4d_hint(dst + (uint32_t)p.qoff + half_bytes, &tm_w, bar, c * 64, 1, 0, zb, pol_w);
-          if (mixed_tail) tma_load_3d_hint(dst, &tm_xt, bar, c * 64, tile_rows, b, pol_last);
+          if (mixed_tail) tma_load_3d_hint(dst, &tm_xt, bar, c * 64, tile_rows, b, pol_x);
           if (p.pf > 0) {                                          // the chunk pf ahead (maybe of the next sample) -> L2
             int cp = c + p.pf, bp = b;
             if (cp >= c_lo + nch) { cp -= nch; bp += ncta; }
@@ -528,25 +533,42 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     };
     // 16 queries (j0 ..) of this lane's token n -> the bf16 hi / lo operand rows of its 64-token block.  Conversions
     // are the packed kind (two values per instruction on the FMA pipe; the single-value F2F runs on the 16-lane XU
-    // pipe and was the epilogue's bottleneck together with the exp), rows m >= M are left alone (they stay zero)
+    // pipe).  2-byte shared-memory stores were the slowest part of the epilogue (32 per unit and lane), so the values
+    // go through an 8 x 8 transpose of query pairs among the 8 lanes of a group first: lane j ends with queries 2j,
+    // 2j + 1 of the group's 8 consecutive tokens = one 16-byte swizzle segment per row.  Rows m >= M stay zero.
     auto store_rows = [&](int n0, int n, int j0, const float (&x)[16]) {
-      uint8_t* rowb = blk_gen + (size_t)(n0 >> 6) * 2u * half_bytes + (uint32_t)j0 * 128u + (uint32_t)(n & 7) * 2u;
-      const uint32_t c3 = ((uint32_t)n & 63u) >> 3;
+      (void)n;
+      uint32_t hp[8], lp[8];
 #pragma unroll
-      for (int q = 0; q < 16; q += 2) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[q], x[q + 1]);
-        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[q] - __uint_as_float(hb << 16), x[q + 1] - __uint_as_float(hb & 0xffff0000u));
-        const uint32_t lb = *reinterpret_cast<const uint32_t*>(&l2);
-        const uint32_t off0 = (uint32_t)q * 128u + ((c3 ^ (uint32_t)(q & 7)) << 4);
-        const uint32_t off1 = (uint32_t)(q + 1) * 128u + ((c3 ^ (uint32_t)((q + 1) & 7)) << 4);
-        if (j0 + q < p.M) {                                        // warp-uniform
-          *reinterpret_cast<unsigned short*>(rowb + off0) = (unsigned short)hb;
-          *reinterpret_cast<unsigned short*>(rowb + half_bytes + off0) = (unsigned short)lb;
+      for (int pr = 0; pr < 8; ++pr) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * pr], x[2 * pr + 1]);
+        hp[pr] = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * pr] - __uint_as_float(hp[pr] << 16), x[2 * pr + 1] - __uint_as_float(hp[pr] & 0xffff0000u));
+        lp[pr] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+#pragma unroll
+      for (int st = 4; st >= 1; st >>= 1) {
+        const bool up = (lane & st) != 0;
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) {
+          if (pr & st) continue;
+          const uint32_t sh = __shfl_xor_sync(0xffffffffu, up ? hp[pr] : hp[pr | st], st);
+          const uint32_t sl = __shfl_xor_sync(0xffffffffu, up ? lp[pr] : lp[pr | st], st);
+          if (up) { hp[pr] = sh; lp[pr] = sl; } else { hp[pr | st] = sh; lp[pr | st] = sl; }
         }
-        if (j0 + q + 1 < p.M) {
-          *reinterpret_cast<unsigned short*>(rowb + off1) = (unsigned short)(hb >> 16);
-          *reinterpret_cast<unsigned short*>(rowb + half_bytes + off1) = (unsigned short)(lb >> 16);
+      }
+      uint8_t* blk = blk_gen + (size_t)(n0 >> 6) * 2u * half_bytes;
+      const uint32_t c3 = (((uint32_t)n0 & 63u) >> 3) + (uint32_t)(lane >> 3);   // the group's 16-byte segment of a row
+#pragma unroll
+      for (int hq = 0; hq < 2; ++hq) {
+        const uint32_t m = (uint32_t)j0 + 2u * (uint32_t)(lane & 7) + (uint32_t)hq;
+        if ((int)m < p.M) {
+          const uint32_t sel = hq ? 0x7632u : 0x5410u;
+          const uint32_t off = m * 128u + ((c3 ^ (m & 7u)) << 4);
+          *reinterpret_cast<uint4*>(blk + off) = make_uint4(__byte_perm(hp[0], hp[1], sel), __byte_perm(hp[2], hp[3], sel),
+                                                            __byte_perm(hp[4], hp[5], sel), __byte_perm(hp[6], hp[7], sel));
+          *reinterpret_cast<uint4*>(blk + half_bytes + off) = make_uint4(__byte_perm(lp[0], lp[1], sel), __byte_perm(lp[2], lp[3], sel),
+                                                                         __byte_perm(lp[4], lp[5], sel), __byte_perm(lp[6], lp[7], sel));
         }
       }
     };
@@ -701,6 +723,7 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (has_hi) psum[ew * SW + 32 + lane] = 0.f;
         __syncwarp();
         wait_blocks_free();
+        if (warp == 4) EP_TRACE(i, 5);                             // (dev) pass 2 begins
         // ---- pass 2: exp, row sums and the operand blocks of the pooled phase: what the P warp waits for.  Straight-line
         // code, the 16 queries of a unit are independent chains
         auto unit_exp = [&](int t, int j0, const float (&x)[16]) {
@@ -715,9 +738,11 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const float ex = ex2_ftz(fmaf(x[q], kLog2e, -mxs));
             e[q] = (valid && m < p.M) ? ex : 0.f;
           }
-          store_rows(n0, n, j0, e);
-          const float red = reduce16<false>(e, lane);
-          if ((lane & 1) == 0) psum[ew * SW + j0 + ridx] += red;
+          if (!(kDev && (p.skip & 1))) store_rows(n0, n, j0, e);
+          if (!(kDev && (p.skip & 2))) {
+            const float red = reduce16<false>(e, lane);
+            if ((lane & 1) == 0) psum[ew * SW + j0 + ridx] += red;
+          } else if (lane == 0) psum[ew * SW + j0] += e[0];
           __syncwarp();
         };
 #pragma unroll
@@ -866,7 +891,7 @@ int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 struct FPlan {
   bool ok = false;
   int Mp, ntiles, nfull, tail_rows, nchunks, nkb, nsl, nL, nP, lbytes, nkp, pf, lead, nbuf, bufcols, pcol0, tmem_cols, qoff, toff, nslg, G, pbufcols;
-  int lsplit, lcolw, kl, last_rows, pair, nslA;
+  int lsplit, lcolw, kl, last_rows, pair, nslA, nstream;
   size_t smem;
 };
 
@@ -944,6 +969,10 @@ FPlan make_fplan(int N, int D, int M, int ctas, bool bwd) {
   if (pl.nbuf == 1) pl.lead = 0;                                  // a lead needs the second logit buffer
   const size_t budget = kL2Budget + ((size_t)((g_debug >> 25) & 7) * 10 << 20);   // dev knob: bits 25-27 = +10 MB each
   while (pl.lead > 1 && sample * live * (nchc + pl.lead) / nchc > budget) --pl.lead;
+  // the first quarter of a sample's chunks is re-read last (the pooled phase walks D downwards) and is what L2 loses
+  // when the live set does not fit: fetched evict_first, it leaves the room to the rest (c2: backward 192 -> 188 us,
+  // c3: 211 -> 203 us; forward within 1 %).  dev knob: bits 0-3 = chunks + 1
+  pl.nstream = (g_debug & 15) ? std::min(nchc, (g_debug & 15) - 1) : nchc / 4;
   pl.ok = true;
   return pl;
 }
@@ -992,12 +1021,12 @@ int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int 
   p.B = B; p.N = N; p.D = D; p.M = M; p.Mp = pl.Mp;
   p.ntiles = pl.ntiles; p.nfull = pl.nfull; p.tail_rows = pl.tail_rows;
   p.nchunks = pl.nchunks; p.nkb = pl.nkb; p.nsl = pl.nsl; p.nL = pl.nL; p.nP = pl.nP; p.lbytes = pl.lbytes; p.nkp = pl.nkp; p.pf = pl.pf;
-  p.lead = pl.lead; p.nbuf = pl.nbuf;
+  p.lead = pl.lead; p.nbuf = pl.nbuf; p.nstream = pl.nstream;
   p.nslg = pl.nslg; p.G = pl.G; p.pbufcols = pl.pbufcols; p.lsplit = pl.lsplit; p.lcolw = pl.lcolw; p.kl = pl.kl;
   p.last_rows = pl.last_rows; p.pair = pl.pair; p.nslA = pl.nslA;
-  p.trace = (g_debug & 2048) ? 1 : 0; p.nomma = (g_debug & 4096) ? 1 : 0; p.noepi = (g_debug & 8192) ? 1 : 0;
+  p.trace = (g_debug & 2048) ? 1 : 0; p.nomma = (g_debug & 4096) ? 1 : 0; p.noepi = (g_debug & 8192) ? 1 : 0; p.skip = (g_debug >> 14) & 3;
   p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff; p.toff = pl.toff;
-  if (p.trace || p.nomma || p.noepi || p.pair) {                  // developer knobs: the instrumented instantiation
+  if (p.trace || p.nomma || p.noepi || p.pair || p.skip) {                  // developer knobs: the instrumented instantiation
     if ((rc = set_smem(fused_kernel<kBwd, true>, pl.smem))) return rc;
     fused_kernel<kBwd, true><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
   } else {

@@ -70,9 +70,10 @@ int ep_last_kernel_family(void);
  * CUDA events on the call's stream (one host sync per call) and record the durations, read back with
  * ep_timing_*; bit 8 (256) also prints them; bit 9 (512) runs the forward softmax as a separate kernel instead
  * of in the logit kernel's epilogue (same results); bit 10 (1024) selects the two-kernel path per direction
- * instead of the one-pass kernels (same results; cross-check).  Bits 11-13 and 16-29 select the instrumented
- * instantiation of the one-pass kernels (pipeline stamps, timing experiments whose RESULTS ARE GARBAGE, plan
- * overrides: csrc/ep_fused_sm100.cu).  0 in normal use. */
+ * instead of the one-pass kernels (same results; cross-check).  Bits 0-3 and 16-27 override the one-pass kernels'
+ * plan (same results), bits 11-15 and 28-29 select their instrumented
+ * instantiation (pipeline stamps, pair mode, timing experiments whose RESULTS ARE GARBAGE): csrc/ep_fused_sm100.cu.
+ * 0 in normal use. */
 int ep_set_debug(int flags);
 int ep_timing_count(void);
 int ep_timing_get(int i, char* name, int name_len, float* microseconds);

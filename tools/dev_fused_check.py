@@ -111,7 +111,7 @@ def trace(B, N, D, M, bwd=False, flags=0):
     lib.ep_debug_trace(ctypes.cast(buf, ctypes.c_void_p), 128)
     t = [buf[i] for i in range(128)]
     t0 = min(v for v in t[:112] if v > 0)
-    names = {0: "P:wait_blocks", 1: "P:start", 3: "P:issued", 2: "L:issued", 4: "epi:pass1", 5: "u0:pre", 6: "u0:loaded", 7: "u0:stored", 11: "u0:summed", 8: "epi:begin", 9: "epi:logits_ready",
+    names = {0: "P:wait_blocks", 1: "P:start", 3: "P:issued", 2: "L:issued", 4: "epi:pass1", 5: "epi:pass2_begin", 8: "epi:begin", 9: "epi:logits_ready",
              10: "epi:P_prev_done", 12: "epi:blocks_written", 13: "epi:drains_done"}
     print(f"trace {'bwd' if bwd else 'fwd'} B{B} N{N} D{D} M{M}")
     for i in range(2, 5):
