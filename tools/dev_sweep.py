@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import efficient_probing_b200 as E
 
-CFG = {"c1": (64, 197, 768), "c2": (1024, 257, 1024), "c3": (1024, 256, 1152), "c4": (1024, 730, 1664), "c5": (1024, 201, 4096)}
+CFG = {"c1": (64, 197, 768), "c2": (1024, 257, 1024), "c3": (1024, 256, 1152), "c4": (1024, 730, 1664), "c5": (1024, 201, 4096),
+       "t128": (2048, 128, 1024), "t256": (1024, 256, 1024), "t64": (4096, 64, 1024)}   # L2 experiments: same bytes, shorter samples
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 limits = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 132, 120, 112, 104, 96, 88, 80, 74]
