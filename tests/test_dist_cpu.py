@@ -34,8 +34,9 @@ def _worker(rank, world, port, out_q):
     allreduce_sum_(flat, None, 0, lay.early)                # the early part first, then the queries
     allreduce_sum_(flat, None, lay.early)
     flat *= 1.0 / world                                     # what the LARS kernel's grad_scale does
-    out_q.put((rank, lay.early, lay.total, {k: t.clone() for k, t in lay.views(flat).items()},
-               {k: r[k] for k in r if k.startswith("grad.")}))
+    # numpy arrays are pickled by value: a tensor would travel as a file descriptor that dies with this process
+    out_q.put((rank, lay.early, lay.total, {k: t.detach().numpy().copy() for k, t in lay.views(flat).items()},
+               {k: r[k].detach().numpy().copy() for k in r if k.startswith("grad.")}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,6 +52,8 @@ def test_two_rank_flat_allreduce_matches_ddp_average():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [(a, b, c, {k: torch.from_numpy(v) for k, v in d.items()}, {k: torch.from_numpy(v) for k, v in e.items()})
+           for a, b, c, d, e in res]
     (_, early, total, avg0, g0), (_, _, _, avg1, g1) = res
     assert early % 64 == 0 and total % 64 == 0
     for k, key in [("fc_w", "grad.2.weight"), ("fc_b", "grad.2.bias"), ("v_w", "grad.0.v.weight"), ("cls", "grad.0.cls_token")]:
