@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto, 1 general kernels, 2 tcgen05 only")
+    ap.add_argument("--debug-bits", type=int, default=0, help="ep_set_debug() developer knobs for the whole run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])
@@ -242,6 +243,7 @@ def main():
     B, N, D, K, M = cfg["B"], cfg["N"], cfg["D"], cfg["K"], args.queries
     lib = E._lib.load()
     lib.ep_set_kernel_mode(args.kernel_mode)
+    lib.ep_set_debug(args.debug_bits)
 
     torch.manual_seed(0)                                         # identical init on every rank (DDP broadcast)
     head = E.make_ep_head(D, M, K).to(dev)
@@ -325,7 +327,7 @@ def main():
     alg_bytes = B * N * D * 2
     pool_mod, s = head[0], E._lib.stream_ptr(dev)
     xt = E._lib.x_dtype_code(pool_x[0])
-    lib.ep_set_debug(32)
+    lib.ep_set_debug(32 | args.debug_bits)
     E._lib.kernel_timings()
     reps = 6
     for i in range(reps + 2):
@@ -342,7 +344,7 @@ def main():
         if i == 1:
             E._lib.kernel_timings()                                # drop the warm-up records
     fam = lib.ep_last_kernel_family()
-    lib.ep_set_debug(0)
+    lib.ep_set_debug(args.debug_bits)
     agg = {}
     for nm, us in E._lib.kernel_timings():
         agg.setdefault(nm, []).append(us)
@@ -374,6 +376,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_dict(args, cfg, world),
             "run": {"comm_sms": tr.comm_sms, "cuda_graph": not args.no_graph, "kernel_family": fam,
+                    "operand_copies_by_producers": tr.fuse_ops,
                     "l2": f"inputs larger than L2: {args.pool} resident batches x {alg_bytes / 1e6:.0f} MB cycled",
                     "replica_max_abs_diff": replica_diff},
             "clocks": clocks,

@@ -56,7 +56,24 @@ _SIGNATURES = {
     "ep_adamw_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ep_sgd_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ep_lars_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    # ABI 2: operand copies written by their producers (the *_ops variants; trailing `ops` bitmask)
+    "ep_refresh_operands": (c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p, c_int,
+                                                                                  c_void_p, c_size_t, c_void_p]),
+    "ep_fwd_ops": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 5 +
+                   [c_void_p] * 6 + [c_void_p, c_size_t, c_int, c_void_p]),
+    "ep_bwd_proj_ops": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "ep_bn_fwd_ops": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int] + [c_void_p] * 6 +
+                      [c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ep_bn_bwd_ops": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5 +
+                      [c_void_p, c_size_t, c_int, c_void_p]),
+    "ep_linear_fwd_ops": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_int,
+                                  c_void_p]),
+    "ep_linear_bwd_ops": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_int, c_void_p]),
+    "ep_ce_fwd_bwd_ops": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
 }
+EP_OPS_WEIGHTS, EP_OPS_INPUT, EP_OPS_FP32 = 1, 2, 4
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
@@ -79,7 +96,7 @@ def load(build_if_missing=True):
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here == the ABI and the header disagree
             fn.restype, fn.argtypes = res, args
-        if lib.ep_abi_version() != 1:
+        if lib.ep_abi_version() != 2:
             raise EPError("libep_b200.so ABI version mismatch")
         _lib = lib
         return lib

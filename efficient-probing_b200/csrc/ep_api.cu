@@ -12,6 +12,14 @@ namespace ep { extern int g_debug; }
 static int g_gemm_mode = 0;                   // 0 = tensor cores (3-term bf16 / TF32 products), 1 = fp32 CUDA cores
 static int g_kernel_mode = 0;                 // 0 auto, 1 general, 2 tcgen05
 static thread_local int t_last_family = 0;
+static thread_local int t_fp32_gemm = 0;      // EP_OPS_FP32 of the *_ops call running on this thread
+namespace {
+struct OpsScope {                             // per-call, per-thread GEMM mode of the *_ops entry points
+  int saved;
+  explicit OpsScope(int ops) : saved(t_fp32_gemm) { if (ops & EP_OPS_FP32) t_fp32_gemm = 1; }
+  ~OpsScope() { t_fp32_gemm = saved; }
+};
+}  // namespace
 
 extern "C" int ep_abi_version(void) { return EP_ABI_VERSION; }
 
@@ -75,14 +83,14 @@ extern "C" unsigned long long ep_launch_count(void) { return ep::g_launch_count;
 
 namespace {
 struct Ws {                      // workspace layout
-  size_t dP, delta, slots, sm100, w_t, g_r, g_t, total;
+  size_t dP, delta, slots, sm100, w_t, w_p, g_r, g_t, total;
 };
 // The small GEMMs run on the tensor cores in TF32 unless the developer knob (bit 7) asks for the fp32
 // CUDA-core GEMM; operands are rounded to tf32 (nearest) first so the hardware's truncation is exact.
 // 3-term operand copies of the K-concatenated GEMMs: bf16 hi/lo (kind::f16, half the bytes, twice the MMA
 // rate) rather than tf32 big/small; both give ~1e-5.  bf16 rows need K % 8 == 0 for 16-byte TMA strides.
 constexpr int kSplitBf16 = 1;
-bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0; }
+bool use_tc() { return gemm_tc_available() && g_gemm_mode == 0 && !t_fp32_gemm; }
 int round_nt(int c) { return std::min(256, (c + 31) / 32 * 32); }
 // column tile of the classifier GEMMs: the narrowest that still gives every SM a tile
 int lin_nt(int rows, int cols) {
@@ -96,6 +104,7 @@ Ws carve(int B, int N, int D, int M) {
   Ws w;
   size_t off = 0;
   w.w_t = off;   off += align_up((size_t)3 * D * D * sizeof(float), 256);   // 3xTF32 copy of v_w^T per query
+  w.w_p = off;   off += align_up((size_t)3 * D * D * 2, 256);               // bf16 [hi|hi|lo] copy of v_w (projection)
   w.g_r = off;   off += align_up((size_t)3 * B * D * sizeof(float), 256);   // 3xTF32 copy of g_out
   w.g_t = off;   off += align_up((size_t)3 * B * D * 2, 256);               // bf16 [hi|hi|lo] copy of g_out^T
   w.dP = off;    off += align_up((size_t)B * M * D * sizeof(float), 256);
@@ -147,7 +156,8 @@ namespace {
 // general = 1: the general kernel family with fp32 P whatever the mode (ep_fwd_ex)
 int fwd_impl(const void* x, int x_dtype, const float* cls_token, int cls_batched, int general, const float* v_w,
              const float* v_b, float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
-             float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+             float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, void* stream, int ops = 0) {
+  OpsScope scope(ops);
   int rc = check_common(x, x_dtype, cls_token, B, N, D, M, d_out);
   if (rc) return rc;
   if (!v_w || !out || !S || !rowmax || !rowsum || !P) return EP_ERR_NULL;
@@ -158,7 +168,7 @@ int fwd_impl(const void* x, int x_dtype, const float* cls_token, int cls_batched
   if (!general && use_sm100(x_dtype, B, N, D, M, &rc)) {
     t_last_family = 2;
     rc = sm100_pool_fwd(x, cls_token, scale, B, N, D, M, P, S, rowmax, rowsum, attn, round_p,
-                        (char*)workspace + w.sm100, s);
+                        (char*)workspace + w.sm100, s, (ops & EP_OPS_WEIGHTS) ? 1 : 0);
   } else {
     if (rc) return rc;
     t_last_family = 1;
@@ -170,10 +180,12 @@ int fwd_impl(const void* x, int x_dtype, const float* cls_token, int cls_batched
   if (round_p) {
     // tcgen05 3-term bf16 GEMM: A = P's hi/lo rows read in place, B = [W_hi | W_hi | W_lo] (a 6*D'*D-byte copy
     // whose first and last thirds are the hi/lo pair)
-    void* w3f = (char*)workspace + w.w_t;
+    void* w3f = (char*)workspace + w.w_p;
     StageTimer tm(s);
-    if ((rc = launch_split3(v_w, w3f, Dp, D, D, D, 1, 1, s))) return rc;
-    tm.mark("proj split3 W");
+    if (!(ops & EP_OPS_WEIGHTS)) {
+      if ((rc = launch_split3(v_w, w3f, Dp, D, D, D, 1, 1, s))) return rc;
+      tm.mark("proj split3 W");
+    }
     const unsigned long long D3 = 3ull * D;
     TcSide A{P, (unsigned long long)D, 2ull * M, (unsigned long long)B, (unsigned long long)D, 2ull * M * D, TC_KMAJOR, 1, 1,
              1, 2, 1, 0};
@@ -201,6 +213,14 @@ extern "C" int ep_fwd(const void* x, int x_dtype, const float* cls_token, const 
                   workspace, workspace_bytes, stream);
 }
 
+extern "C" int ep_fwd_ops(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
+                          float scale, int B, int N, int D, int M, int d_out, float* out, float* S, float* rowmax,
+                          float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes, int ops,
+                          void* stream) {
+  return fwd_impl(x, x_dtype, cls_token, 0, 0, v_w, v_b, scale, B, N, D, M, d_out, out, S, rowmax, rowsum, P, attn,
+                  workspace, workspace_bytes, stream, ops);
+}
+
 extern "C" int ep_fwd_ex(const void* x, int x_dtype, const float* cls_token, int cls_batched, const float* v_w,
                          const float* v_b, float scale, int B, int N, int D, int M, int d_out, float* out, float* S,
                          float* rowmax, float* rowsum, float* P, float* attn, void* workspace, size_t workspace_bytes,
@@ -212,7 +232,7 @@ extern "C" int ep_fwd_ex(const void* x, int x_dtype, const float* cls_token, int
 namespace {
 int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_dp, const float* out, const float* v_w,
                   const float* v_b, int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
-                  void* workspace, size_t workspace_bytes, void* stream);
+                  void* workspace, size_t workspace_bytes, void* stream, int ops = 0);
 }
 extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out, const float* v_w, const float* v_b,
                            int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
@@ -220,13 +240,20 @@ extern "C" int ep_bwd_proj(const float* g_out, const float* P, const float* out,
   return bwd_proj_impl(g_out, P, -1, 0, out, v_w, v_b, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace,
                        workspace_bytes, stream);
 }
+extern "C" int ep_bwd_proj_ops(const float* g_out, const float* P, const float* out, const float* v_w, const float* v_b,
+                               int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
+                               void* workspace, size_t workspace_bytes, int ops, void* stream) {
+  return bwd_proj_impl(g_out, P, -1, 0, out, v_w, v_b, x_dtype, B, N, D, M, d_out, d_v_w, d_v_b, workspace,
+                       workspace_bytes, stream, ops);
+}
 
 namespace {
 // p_layout: -1 = what ep_fwd produces for this shape and mode, else 0 (fp32) / 1 (bf16 hi/lo rows);
 // general_dp = 1: dP is written as fp32 (B, M, D) for the general pooling kernels whatever the family
 int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_dp, const float* out, const float* v_w,
                   const float* v_b, int x_dtype, int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
-                  void* workspace, size_t workspace_bytes, void* stream) {
+                  void* workspace, size_t workspace_bytes, void* stream, int ops) {
+  OpsScope scope(ops);
   if (!g_out || !P || !out || !v_w || !d_v_w) return EP_ERR_NULL;
   if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
   const Ws w = carve(B, N, D, M);
@@ -238,7 +265,9 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
   int rc;
   StageTimer tm(s);
   // delta[b, m] = sum_n A dA = dP[b, m] . P[b, m] = g[b, m, :] . (out[b, m, :] - bias[m, :])
-  if ((rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
+  // (EP_OPS_INPUT: ep_bn_bwd_ops left delta and the copies of g_out in the workspace -- g_ops_kernel, ep_ops.cu)
+  const bool g_ready = (ops & EP_OPS_INPUT) != 0, w_ready = (ops & EP_OPS_WEIGHTS) != 0;
+  if (!g_ready && (rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
   const bool hilo = p_layout < 0 ? p_hilo(x_dtype, B, N, D, M, d_out) : p_layout == 1;
   if (hilo && !(use_tc() && c % 4 == 0 && B % 64 == 0 && D % 64 == 0)) return EP_ERR_UNSUPPORTED;   // mode changed since ep_fwd
   if (use_tc() && c % 4 == 0) {
@@ -247,8 +276,10 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
       // tcgen05 3-term bf16 GEMM: rows d, cols j, contraction over b.  A = P's hi/lo rows in place, MN-major
       // (channels contiguous); B = g^T as [g_hi | g_hi | g_lo] (K-major copy, 6*B*D' bytes)
       void* g3t = (char*)workspace + w.g_t;
-      if ((rc = launch_split3_transpose(g_out, g3t, B, B, Dp, 1, 0, 0, 1, 1, s))) return rc;     // [Dp][3B]
-      tm.mark("dW split3t g");
+      if (!g_ready) {
+        if ((rc = launch_split3_transpose(g_out, g3t, B, B, Dp, 1, 0, 0, 1, 1, s))) return rc;     // [Dp][3B]
+        tm.mark("dW split3t g");
+      }
       const unsigned long long B3 = 3ull * B;
       TcSide A{P, (unsigned long long)D, 2ull * M, (unsigned long long)B, (unsigned long long)D, 2ull * M * D, TC_MNMAJOR, 1,
                1, 1, 2, 1, 0};
@@ -265,8 +296,8 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
       float* g3 = (float*)((char*)workspace + w.g_r);              // [(b, m)][3c]  = [big | small | big]
       float* w3 = (float*)((char*)workspace + w.w_t);              // [m][d][3c]    = [big | big | small]
       const int bf = kSplitBf16 && c % 8 == 0;               // bf16 rows need 16-byte strides: 3c * 2 B
-      if ((rc = launch_split3(g_out, g3, (long long)B * M, c, c, c, 0, bf, s))) return rc;
-      if ((rc = launch_split3_transpose(v_w, w3, c, c, D, M, (long long)c * D, (long long)3 * c * D, 1, bf, s))) return rc;
+      if (!g_ready && (rc = launch_split3(g_out, g3, (long long)B * M, c, c, c, 0, bf, s))) return rc;
+      if (!w_ready && (rc = launch_split3_transpose(v_w, w3, c, c, D, M, (long long)c * D, (long long)3 * c * D, 1, bf, s))) return rc;
       tm.mark("split3 g, W");
       const unsigned long long c3 = 3ull * c;
       TcSide A{g3, c3, (unsigned long long)M, (unsigned long long)B, c3, c3 * M, TC_KMAJOR, 1, 1, bf};
@@ -422,8 +453,13 @@ bool lin_ws(void* ws, size_t bytes, int B, int F, int K, LinWs* o) {
 }
 }  // namespace
 
-extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+namespace {
+// the bf16 copies of BOTH classifier GEMM directions exist (what the *_ops producers write and consumers trust)
+bool lin_ops_ok(int F, int K) { return use_tc() && kSplitBf16 && F % 8 == 0 && K % 8 == 0; }
+
+int linear_fwd_impl(const float* y, const float* W, const float* b, int B, int F, int K, float* logits, void* workspace,
+                    size_t workspace_bytes, int ops, void* stream) {
+  OpsScope scope(ops);
   if (!y || !W || !logits) return EP_ERR_NULL;
   if (B <= 0 || F <= 0 || K <= 0) return EP_ERR_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -435,8 +471,9 @@ extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int
     // thirds of each operand once per stage and issues the three products itself (GemmTC::x3)
     const int bf = kSplitBf16 && F % 8 == 0;
     const int Fp = bf ? (int)pad64(F) : F;
-    if ((rc = launch_split3(W, lw.w_r, K, F, Fp, F, 1, bf, s))) return rc;
-    if ((rc = launch_split3(y, lw.y_r, B, F, Fp, F, 0, bf, s))) return rc;
+    const bool ready = lin_ops_ok(F, K);                        // else the flags are ignored: self-made copies
+    if (!(ready && (ops & EP_OPS_WEIGHTS)) && (rc = launch_split3(W, lw.w_r, K, F, Fp, F, 1, bf, s))) return rc;
+    if (!(ready && (ops & EP_OPS_INPUT)) && (rc = launch_split3(y, lw.y_r, B, F, Fp, F, 0, bf, s))) return rc;
     tm.mark("lin split3 W,y");
     const unsigned long long F3 = 3ull * Fp;
     TcSide A{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_KMAJOR, 0, 1, bf, 1, 0, bf ? Fp : 0};
@@ -452,8 +489,9 @@ extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int
   return launch_gemm_v0(g, s);
 }
 
-extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* W, int B, int F, int K, float* dW,
-                             float* db, float* dy, void* workspace, size_t workspace_bytes, void* stream) {
+int linear_bwd_impl(const float* dlogits, const float* y, const float* W, int B, int F, int K, float* dW, float* db,
+                    float* dy, void* workspace, size_t workspace_bytes, int ops, void* stream) {
+  OpsScope scope(ops);
   if (!dlogits) return EP_ERR_NULL;
   if (B <= 0 || F <= 0 || K <= 0) return EP_ERR_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -462,10 +500,20 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
   LinWs lw;
   const bool aligned = use_tc() && F % 4 == 0 && K % 4 == 0;
   const bool tc = aligned && lin_ws(workspace, workspace_bytes, B, F, K, &lw);   // dy needs the operand copies
-  (void)0;
+  const bool ready = tc && lin_ops_ok(F, K);
   if (dW) {
     if (!y) return EP_ERR_NULL;
-    if (aligned) {                 // dW[k, f] = sum_b dlogits[b, k] * y[b, f]: batch-major operands, "TN" kernel
+    if (ready && (ops & EP_OPS_INPUT) && !(g_debug & (1 << 30))) {
+      // dW[k, f] = sum_b dlogits[b, k] * y[b, f] on tcgen05: both operands are batch-major, i.e. MN-major (output index
+      // contiguous), and their [hi | lo | hi] copies already exist (written by ep_ce_fwd_bwd_ops / ep_bn_fwd_ops); the
+      // lo tile of a stage is the hi tile's box shifted by one third along the row
+      const int Fp = (int)pad64(F), Kp = (int)pad64(K);
+      const unsigned long long K3 = 3ull * Kp, F3 = 3ull * Fp;
+      TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_MNMAJOR, 0, 1, 1, 1, 0, 0, Kp};
+      TcSide Bm{lw.y_r, F3, (unsigned long long)B, 1ull, F3, F3 * B, TC_MNMAJOR, 0, 1, 1, 0, 0, 0, Fp};
+      if ((rc = tc_gemm(A, Bm, K, F, B, 1, 64, dW, F, 1, 0, nullptr, 0, 0, s))) return rc;
+      tm.mark("lin dW tc-gemm");
+    } else if (aligned) {          // batch-major operands as they lie: mma.sync TF32 "TN" kernel
       if ((rc = launch_gemm_tn(dlogits, y, dW, K, F, B, 1, K, F, F, 0, 0, 0, s))) return rc;
       tm.mark("lin dW tn-gemm");
     } else {
@@ -482,8 +530,9 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
     if (tc) {                      // dy[b, f] = sum_k dlogits[b, k] * W[k, f]: tcgen05, 3xTF32, transposed weight copy
       const int bf = kSplitBf16 && K % 8 == 0;
       const int Kp = bf ? (int)pad64(K) : K;
-      if ((rc = launch_split3(dlogits, lw.d_r, B, K, Kp, K, 0, bf, s))) return rc;                // [b][3Kp]
-      if ((rc = launch_split3_transpose(W, lw.w_t, K, Kp, F, 1, 0, 0, 1, bf, s))) return rc;      // [f][3Kp]
+      if (!(ready && (ops & EP_OPS_INPUT)) && (rc = launch_split3(dlogits, lw.d_r, B, K, Kp, K, 0, bf, s))) return rc;   // [b][3Kp]
+      if (!(ready && (ops & EP_OPS_WEIGHTS)) && (rc = launch_split3_transpose(W, lw.w_t, K, Kp, F, 1, 0, 0, 1, bf, s)))
+        return rc;                                                                                                   // [f][3Kp]
       tm.mark("lin split3 dl,Wt");
       const unsigned long long K3 = 3ull * Kp;
       TcSide A{lw.d_r, K3, (unsigned long long)B, 1ull, K3, K3 * B, TC_KMAJOR, 0, 1, bf, 1, 0, bf ? Kp : 0};
@@ -499,4 +548,117 @@ extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* 
     }
   }
   return 0;
+}
+}  // namespace
+
+extern "C" int ep_linear_fwd(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return linear_fwd_impl(y, W, b, B, F, K, logits, workspace, workspace_bytes, 0, stream);
+}
+extern "C" int ep_linear_fwd_ops(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
+                                 void* workspace, size_t workspace_bytes, int ops, void* stream) {
+  return linear_fwd_impl(y, W, b, B, F, K, logits, workspace, workspace_bytes, ops, stream);
+}
+extern "C" int ep_linear_bwd(const float* dlogits, const float* y, const float* W, int B, int F, int K, float* dW,
+                             float* db, float* dy, void* workspace, size_t workspace_bytes, void* stream) {
+  return linear_bwd_impl(dlogits, y, W, B, F, K, dW, db, dy, workspace, workspace_bytes, 0, stream);
+}
+extern "C" int ep_linear_bwd_ops(const float* dlogits, const float* y, const float* W, int B, int F, int K, float* dW,
+                                 float* db, float* dy, void* workspace, size_t workspace_bytes, int ops, void* stream) {
+  return linear_bwd_impl(dlogits, y, W, B, F, K, dW, db, dy, workspace, workspace_bytes, ops, stream);
+}
+
+// ---- producers of the operand copies (ABI 2) -------------------------------------------------------------------
+
+extern "C" int ep_bn_fwd_ops(const float* h, int B, int F, float eps, float momentum, int training, float* running_mean,
+                             float* running_var, long long* nbt, float* y, float* save_mean, float* save_invstd, int K,
+                             void* lin_workspace, size_t lin_workspace_bytes, int ops, void* stream) {
+  OpsScope scope(ops);
+  if (!h || !y || !running_mean || !running_var) return EP_ERR_NULL;
+  if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
+  LinWs lw;
+  void* y3 = nullptr;
+  if (lin_workspace && K > 0 && lin_ops_ok(F, K) && lin_ws(lin_workspace, lin_workspace_bytes, B, F, K, &lw)) y3 = lw.y_r;
+  return launch_bn_fwd(h, B, F, eps, momentum, training, running_mean, running_var, nbt, y, save_mean, save_invstd, y3,
+                       (int)pad64(F), (cudaStream_t)stream);
+}
+
+extern "C" int ep_ce_fwd_bwd_ops(const float* logits, const long long* targets, int B, int K, float loss_scale,
+                                 float grad_scale, float* step_loss, float* loss_acc, float* dlogits, int* correct,
+                                 float* scratch, int F, void* lin_workspace, size_t lin_workspace_bytes, int ops,
+                                 void* stream) {
+  OpsScope scope(ops);
+  if (!logits || !targets || !scratch) return EP_ERR_NULL;
+  if (B <= 0 || K <= 0) return EP_ERR_SHAPE;
+  LinWs lw;
+  void* d3 = nullptr;
+  if (dlogits && lin_workspace && F > 0 && lin_ops_ok(F, K) && lin_ws(lin_workspace, lin_workspace_bytes, B, F, K, &lw))
+    d3 = lw.d_r;
+  return launch_ce(logits, targets, B, K, loss_scale, grad_scale, step_loss, dlogits, correct, d3, (int)pad64(K), scratch,
+                   loss_acc, (cudaStream_t)stream);
+}
+
+extern "C" int ep_bn_bwd_ops(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh,
+                             const float* out, const float* v_b, int x_dtype, int N, int D, int M, int d_out,
+                             void* workspace, size_t workspace_bytes, int ops, void* stream) {
+  OpsScope scope(ops);
+  if (!dy || !y || !save_invstd || !dh || !out) return EP_ERR_NULL;
+  if (B <= 0 || F <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0 || F != D / d_out)
+    return EP_ERR_SHAPE;
+  const Ws w = carve(B, N, D, M);
+  if (!workspace || workspace_bytes < w.total) return EP_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = launch_bn_bwd(dy, y, save_invstd, B, F, dh, s))) return rc;
+  // what bwd_proj_impl would derive from dh = g_out, by the same predicates
+  const int c = F / M;
+  const bool tc = use_tc() && c % 4 == 0;
+  const bool hilo = p_hilo(x_dtype, B, N, D, M, d_out);
+  const int bf = kSplitBf16 && c % 8 == 0;
+  return launch_g_ops(dh, out, v_b, B, M, c, (float*)((char*)workspace + w.delta), tc ? (char*)workspace + w.g_r : nullptr, bf,
+                      (tc && hilo) ? (char*)workspace + w.g_t : nullptr, s);
+}
+
+extern "C" int ep_refresh_operands(const float* cls_token, const float* v_w, float scale, int x_dtype, int B, int N, int D,
+                                   int M, int d_out, void* workspace, size_t workspace_bytes, const float* fc_w, int K,
+                                   void* lin_workspace, size_t lin_workspace_bytes, void* stream) {
+  if (!cls_token || !v_w) return EP_ERR_NULL;
+  if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
+  const Ws w = carve(B, N, D, M);
+  if (!workspace || workspace_bytes < w.total) return EP_ERR_WORKSPACE;
+  const int Dp = D / d_out, c = Dp / M;
+  RefreshJob jobs[kMaxRefreshJobs];
+  int n = 0, rc = 0;
+  if (use_sm100(x_dtype, B, N, D, M, &rc)) {           // scaled queries as hi/lo rows (one-pass forward, logit kernels)
+    RefreshJob j{};
+    j.type = REFRESH_HILO; j.src = cls_token; j.dst = sm100_qhl_ptr((char*)workspace + w.sm100, B, N, D, M);
+    j.scale = scale; j.M = M; j.J = sm100_J(N, D, M); j.D = D;
+    jobs[n++] = j;
+  }
+  if (p_hilo(x_dtype, B, N, D, M, d_out)) {            // projection: [hi | hi | lo] rows of v.weight
+    RefreshJob j{};
+    j.type = REFRESH_ROWS; j.src = v_w; j.dst = (char*)workspace + w.w_p;
+    j.R = Dp; j.K = D; j.Kp = D; j.ld = D; j.kind = 1; j.bf16 = 1;
+    jobs[n++] = j;
+  }
+  if (use_tc() && c % 4 == 0) {                        // dP = g . W_m: per-query transposed [hi | hi | lo] rows [m][d][3c]
+    RefreshJob j{};
+    j.type = REFRESH_TRANSPOSE; j.src = v_w; j.dst = (char*)workspace + w.w_t;
+    j.K = c; j.Kp = c; j.R = D; j.Z = M; j.src_z = (long long)c * D; j.dst_z = (long long)3 * c * D;
+    j.kind = 1; j.bf16 = kSplitBf16 && c % 8 == 0;
+    jobs[n++] = j;
+  }
+  LinWs lw;
+  if (fc_w && K > 0 && lin_ops_ok(Dp, K) && lin_ws(lin_workspace, lin_workspace_bytes, B, Dp, K, &lw)) {
+    const int Fp = (int)pad64(Dp), Kp = (int)pad64(K);
+    RefreshJob j{};                                     // logits: [hi | hi | lo] rows of fc.weight, thirds padded to Fp
+    j.type = REFRESH_ROWS; j.src = fc_w; j.dst = lw.w_r;
+    j.R = K; j.K = Dp; j.Kp = Fp; j.ld = Dp; j.kind = 1; j.bf16 = 1;
+    jobs[n++] = j;
+    RefreshJob t{};                                     // dy: fc.weight^T as [f][3Kp]
+    t.type = REFRESH_TRANSPOSE; t.src = fc_w; t.dst = lw.w_t;
+    t.K = K; t.Kp = Kp; t.R = Dp; t.Z = 1; t.kind = 1; t.bf16 = 1;
+    jobs[n++] = t;
+  }
+  return launch_refresh(jobs, n, (cudaStream_t)stream);
 }

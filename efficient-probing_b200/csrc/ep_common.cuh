@@ -134,6 +134,7 @@ struct TcSide {            // one operand as a 3-D fp32 tensor (d0 contiguous) a
   // hi/lo operand pair (bf16, 3-term product, see GemmTC::x3): the lo tile is the hi tile's coordinates with
   // batch = z * zmul + lo_z (A side only) and k + lo_k; all zero = plain operand
   int zmul, lo_z, lo_k;
+  int lo_mn;               // MN-major operand with the lo copy in the same row: lo tile = output coordinate + lo_mn
 };
 int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, float* C, long long c_row,
             long long c_col, long long c_z, const float* bias, long long bias_z, int round_out, cudaStream_t s);
@@ -151,6 +152,32 @@ int launch_gemm_nt3(const float* A, const float* B, float* C, const float* bias,
 
 // projection backward with the fused epilogue: dP written as bf16 hi/lo operand rows (B, Jrows, D)
 int tc_gemm_dp(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT, void* hl, int Jrows, cudaStream_t s);
+
+// operand copies written by their producers (ep_ops.cu)
+enum { REFRESH_ROWS = 0, REFRESH_TRANSPOSE = 1, REFRESH_HILO = 2 };
+constexpr int kMaxRefreshJobs = 6;
+struct RefreshJob {
+  int type;
+  const float* src; void* dst;
+  int K, Kp, R, Z;           // ROWS: src [R x K] -> dst [R x 3Kp];  TRANSPOSE: src[z] [K x R] -> dst[z] [R x 3Kp]
+  long long ld, src_z, dst_z;
+  int kind, bf16;            // kind 0: [big|small|big], 1: [big|big|small];  bf16 0: tf32 big/small stored as fp32
+  float scale; int M, J, D;  // HILO: dst [J x D] bf16 rows (2m: hi, 2m + 1: lo) of scale * src [M x D]
+};
+int launch_refresh(const RefreshJob* jobs, int n, cudaStream_t s);
+// delta[b, m] = g[b, m] . (out[b, m] - bias[m]);  g3 (nullable): [(b, m)][3c] A-side copy (bf16, or fp32 tf32 pairs);
+// g3t (nullable): [M c][3B] bf16 B-side copy of g^T
+int launch_g_ops(const float* g, const float* out, const float* bias, int B, int M, int c, float* delta, void* g3,
+                 int g3_bf16, void* g3t, cudaStream_t s);
+
+// head kernels with the optional operand copies of their outputs (ep_epilogue.cu)
+int launch_bn_fwd(const float* h, int B, int F, float eps, float momentum, int training, float* running_mean,
+                  float* running_var, long long* nbt, float* y, float* save_mean, float* save_invstd, void* y3, int Fp,
+                  cudaStream_t s);
+int launch_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, cudaStream_t s);
+int launch_ce(const float* logits, const long long* targets, int B, int K, float loss_scale, float grad_scale,
+              float* loss_sum, float* dlogits, int* correct, void* d3, int Kp, float* scratch, float* loss_acc,
+              cudaStream_t s);
 
 int pool_fwd_v0(const void* x, int x_dtype, const float* cls, float scale, int B, int N, int D, int M,
                 float* P, float* S_out, float* rowmax, float* rowsum, float* attn, int round_p, cudaStream_t s,

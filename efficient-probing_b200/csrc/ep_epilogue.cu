@@ -23,7 +23,10 @@ __device__ __forceinline__ float block_colsum(float v, float (*red)[BN_F + 1]) {
 __global__ void __launch_bounds__(BN_F * BN_Y)
 bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float momentum, int training,
               float* __restrict__ running_mean, float* __restrict__ running_var, long long* nbt,
-              float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+              float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+              __nv_bfloat16* __restrict__ y3, int Fp) {
+  // y3 (nullable): the [hi | lo | hi] bf16 operand copy of y, rows of 3 Fp (thirds zero-padded from F to Fp; the grid
+  // then covers Fp features) -- what the tcgen05 classifier GEMM reads (ep_linear_fwd_ops)
   __shared__ float red[BN_Y][BN_F + 1];
   const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
@@ -48,7 +51,19 @@ bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float moment
     mean = ok ? running_mean[f] : 0.f;
     invstd = ok ? 1.f / sqrtf(running_var[f] + eps) : 0.f;
   }
-  if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) y[(size_t)b * F + f] = (h[(size_t)b * F + f] - mean) * invstd;
+  if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) {
+    const float v = (h[(size_t)b * F + f] - mean) * invstd;
+    y[(size_t)b * F + f] = v;
+    if (y3) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* r = y3 + (size_t)b * 3 * Fp + f;
+      r[0] = hi; r[Fp] = lo; r[2 * Fp] = hi;
+    }
+  } else if (y3 && f < Fp) for (int b = threadIdx.y; b < B; b += BN_Y) {
+    __nv_bfloat16* r = y3 + (size_t)b * 3 * Fp + f;
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    r[0] = z; r[Fp] = z; r[2 * Fp] = z;
+  }
 }
 
 __global__ void __launch_bounds__(BN_F * BN_Y)
@@ -75,7 +90,11 @@ bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const f
 // ---------------- CrossEntropyLoss (mean) fwd+bwd, one CTA per row ----------------
 __global__ void __launch_bounds__(256)
 ce_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, int K, float loss_scale,
-          float grad_scale, float* loss_sum, float* __restrict__ dlogits, int* correct) {
+          float grad_scale, float* loss_sum, float* __restrict__ dlogits, int* correct,
+          __nv_bfloat16* __restrict__ d3, int Kp, float* scratch, float* loss_acc) {
+  // d3 (nullable): the [hi | lo | hi] bf16 operand copy of dlogits, rows of 3 Kp, thirds zero-padded from K to Kp
+  // (ep_linear_bwd_ops).  scratch (nullable): gridDim.x row losses + a counter word -- the last CTA to finish adds the
+  // rows in a fixed order, OVERWRITES loss_sum[0] and adds the value to loss_acc (no zeroing, deterministic)
   __shared__ float redf[8];
   __shared__ int redi[8];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -110,11 +129,47 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target
   const int t = (int)targets[b];
   const float inv = 1.f / s;
   if (dlogits)
-    for (int k = threadIdx.x; k < K; k += 256)
-      dlogits[(size_t)b * K + k] = (expf(row[k] - mx) * inv - (k == t ? 1.f : 0.f)) * grad_scale;
+    for (int k = threadIdx.x; k < (d3 ? Kp : K); k += 256) {
+      const float v = k < K ? (expf(row[k] - mx) * inv - (k == t ? 1.f : 0.f)) * grad_scale : 0.f;
+      if (k < K) dlogits[(size_t)b * K + k] = v;
+      if (d3) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        __nv_bfloat16* r = d3 + (size_t)b * 3 * Kp + k;
+        r[0] = hi; r[Kp] = lo; r[2 * Kp] = hi;
+      }
+    }
+  const float nll = (logf(s) + mx - row[t]) * loss_scale;
+  if (!scratch) {
+    if (threadIdx.x == 0) {
+      if (loss_sum) atomicAdd(loss_sum, nll);
+      if (correct && arg == t) atomicAdd(correct, 1);
+    }
+    return;
+  }
+  __shared__ bool last;
   if (threadIdx.x == 0) {
-    if (loss_sum) atomicAdd(loss_sum, (logf(s) + mx - row[t]) * loss_scale);
     if (correct && arg == t) atomicAdd(correct, 1);
+    scratch[b] = nll;
+    __threadfence();
+    unsigned* counter = reinterpret_cast<unsigned*>(scratch + gridDim.x);
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) acc += __ldcg(scratch + i);   // fixed order: strided, then tree
+  acc = warp_sum(acc);
+  __syncthreads();
+  if (lane == 0) redf[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += redf[w];
+    if (loss_sum) loss_sum[0] = tot;
+    if (loss_acc) loss_acc[0] += tot;
+    *reinterpret_cast<unsigned*>(scratch + gridDim.x) = 0u;
   }
 }
 
@@ -283,8 +338,28 @@ extern "C" int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum
                          void* stream) {
   if (!h || !y || !running_mean || !running_var) return EP_ERR_NULL;
   if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
-  bn_fwd_kernel<<<(F + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, (cudaStream_t)stream>>>(h, B, F, eps, momentum, training, running_mean,
-                                                                         running_var, nbt, y, save_mean, save_invstd);
+  return launch_bn_fwd(h, B, F, eps, momentum, training, running_mean, running_var, nbt, y, save_mean, save_invstd, nullptr, 0,
+                       (cudaStream_t)stream);
+}
+int ep::launch_bn_fwd(const float* h, int B, int F, float eps, float momentum, int training, float* running_mean,
+                      float* running_var, long long* nbt, float* y, float* save_mean, float* save_invstd, void* y3, int Fp,
+                      cudaStream_t s) {
+  const int cols = y3 ? Fp : F;
+  bn_fwd_kernel<<<(cols + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, s>>>(h, B, F, eps, momentum, training, running_mean, running_var,
+                                                                    nbt, y, save_mean, save_invstd, (__nv_bfloat16*)y3, Fp);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+int ep::launch_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, cudaStream_t s) {
+  bn_bwd_kernel<<<(F + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, s>>>(dy, y, save_invstd, B, F, dh);
+  EP_LAUNCH_CHECK();
+  return 0;
+}
+int ep::launch_ce(const float* logits, const long long* targets, int B, int K, float loss_scale, float grad_scale,
+                  float* loss_sum, float* dlogits, int* correct, void* d3, int Kp, float* scratch, float* loss_acc,
+                  cudaStream_t s) {
+  ce_kernel<<<B, 256, 0, s>>>(logits, targets, K, loss_scale, grad_scale, loss_sum, dlogits, correct, (__nv_bfloat16*)d3, Kp,
+                              scratch, loss_acc);
   EP_LAUNCH_CHECK();
   return 0;
 }
@@ -292,18 +367,15 @@ extern "C" int ep_bn_fwd(const float* h, int B, int F, float eps, float momentum
 extern "C" int ep_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, void* stream) {
   if (!dy || !y || !save_invstd || !dh) return EP_ERR_NULL;
   if (B <= 0 || F <= 0) return EP_ERR_SHAPE;
-  bn_bwd_kernel<<<(F + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, (cudaStream_t)stream>>>(dy, y, save_invstd, B, F, dh);
-  EP_LAUNCH_CHECK();
-  return 0;
+  return launch_bn_bwd(dy, y, save_invstd, B, F, dh, (cudaStream_t)stream);
 }
 
 extern "C" int ep_ce_fwd_bwd(const float* logits, const long long* targets, int B, int K, float loss_scale,
                              float grad_scale, float* loss_sum, float* dlogits, int* correct, void* stream) {
   if (!logits || !targets) return EP_ERR_NULL;
   if (B <= 0 || K <= 0) return EP_ERR_SHAPE;
-  ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, targets, K, loss_scale, grad_scale, loss_sum, dlogits, correct);
-  EP_LAUNCH_CHECK();
-  return 0;
+  return launch_ce(logits, targets, B, K, loss_scale, grad_scale, loss_sum, dlogits, correct, nullptr, 0, nullptr, nullptr,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int ep_lars_step(int n, float* const* params, const float* const* grads, float* const* mus,

@@ -34,7 +34,8 @@ struct GemmTC {
   // and issues A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, so each operand byte is fetched once (a [hi|lo|hi] x [hi|hi|lo]
   // concatenation along K would fetch the hi tiles twice).  The lo tile of A sits at batch coordinate + a_lo_z
   // and K coordinate + a_lo_k of the same tensor map, the lo tile of B at K coordinate + b_lo_k.
-  int x3, a_zmul, a_lo_z, a_lo_k, b_lo_k;
+  // (MN-major operands whose lo copy sits in the same row: output coordinate + a_lo_mn / b_lo_mn instead)
+  int x3, a_zmul, a_lo_z, a_lo_k, b_lo_k, a_lo_mn, b_lo_mn;
   float* C; const float* bias;
   long long c_row, c_col, c_z, bias_z;        // element strides of C and bias
   int round_tf32;                             // round the stored result to tf32 (it feeds another TF32 GEMM)
@@ -141,12 +142,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), stage_bytes);
           const int k0 = kc * gk;
-          auto load_pair = [&](uint32_t d, int ka, int zaa, int kb) {
+          auto load_pair = [&](uint32_t d, int ka, int zaa, int kb, int ia, int jb) {
             if (!g.a_mn) {                                     // [128 rows x one 128-byte row of k]
               tma_load_3d(d, &tm_a, full_bar(s), ka, g.a_swap ? zaa : i0, g.a_swap ? i0 : zaa);
             } else {                                           // mn atoms of [gk k-rows x 128 B of mn]
               for (int a = 0; a < mn_atoms; ++a)
-                tma_load_3d(d + (uint32_t)a * atom_bytes, &tm_a, full_bar(s), i0 + mn_elems * a, g.a_swap ? zaa : ka,
+                tma_load_3d(d + (uint32_t)a * atom_bytes, &tm_a, full_bar(s), ia + mn_elems * a, g.a_swap ? zaa : ka,
                             g.a_swap ? ka : zaa);
             }
             const uint32_t bdst = d + a_bytes;
@@ -154,12 +155,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               tma_load_3d(bdst, &tm_b, full_bar(s), kb, g.b_swap ? zb : j0, g.b_swap ? j0 : zb);
             } else {
               for (int a = 0; a < g.NT / mn_elems; ++a)
-                tma_load_3d(bdst + (uint32_t)a * atom_bytes, &tm_b, full_bar(s), j0 + mn_elems * a, g.b_swap ? zb : kb,
+                tma_load_3d(bdst + (uint32_t)a * atom_bytes, &tm_b, full_bar(s), jb + mn_elems * a, g.b_swap ? zb : kb,
                             g.b_swap ? kb : zb);
             }
           };
-          load_pair(dst, k0, za, k0);
-          if (g.x3) load_pair(dst + a_lo_off, k0 + g.a_lo_k, za + g.a_lo_z, k0 + g.b_lo_k);
+          load_pair(dst, k0, za, k0, i0, j0);
+          if (g.x3) load_pair(dst + a_lo_off, k0 + g.a_lo_k, za + g.a_lo_z, k0 + g.b_lo_k, i0 + g.a_lo_mn, j0 + g.b_lo_mn);
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -363,9 +364,10 @@ int tc_gemm(const TcSide& A, const TcSide& B, int I, int J, int K, int Z, int NT
   g.round_tf32 = round_out;
   g.bf16 = A.bf16;
   g.a_zmul = 1;
-  if (A.lo_k || A.lo_z || B.lo_k) {                            // hi/lo operand pairs: 3-term product
+  if (A.lo_k || A.lo_z || B.lo_k || A.lo_mn || B.lo_mn) {                            // hi/lo operand pairs: 3-term product
     if (!A.bf16 || !B.bf16) return EP_ERR_UNSUPPORTED;
     g.x3 = 1; g.a_zmul = A.zmul > 0 ? A.zmul : 1; g.a_lo_z = A.lo_z; g.a_lo_k = A.lo_k; g.b_lo_k = B.lo_k;
+    g.a_lo_mn = A.lo_mn; g.b_lo_mn = B.lo_mn;
   }
   return launch_gemm_tc(ta, tb, g, Z, s);
 }

@@ -889,7 +889,7 @@ size_t sm100_workspace_bytes(int B, int N, int D, int M) {
 }
 
 int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, int D, int M, float* P, float* S,
-                   float* rowmax, float* rowsum, float* attn, int round_p, void* ws, cudaStream_t s) {
+                   float* rowmax, float* rowsum, float* attn, int round_p, void* ws, cudaStream_t s, int q_ready) {
   const Plan pl = make_plan(N, D, M);
   if (!pl.ok) return EP_ERR_UNSUPPORTED;
   const Ws100 w = carve100(B, N, D, M, pl);
@@ -897,9 +897,11 @@ int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, i
   uint8_t* blocks = (uint8_t*)ws + w.dS;
   int rc;
   StageTimer tm(s);
-  split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
-  EP_LAUNCH_CHECK();
-  tm.mark("split_q");
+  if (!q_ready) {          // else: ep_refresh_operands wrote the scaled hi/lo query rows after the last parameter update
+    split_hilo_kernel<<<dim3(std::max(1, pl.J * D / 8 / 256), 1), 256, 0, s>>>(cls, scale, M, pl.J, D, qhl);
+    EP_LAUNCH_CHECK();
+    tm.mark("split_q");
+  }
   // one-pass kernel: logits, softmax and pooled tokens of a sample without leaving the SM (ep_fused_sm100.cu)
   if (attn == nullptr && P != nullptr && !(g_debug & 1024) && fused_supported(N, D, M)) {
     rc = fused_pool_fwd(x, qhl, pl.J, B, N, D, M, P, S, rowmax, rowsum, round_p, (char*)ws + w.fused, s);
@@ -941,6 +943,10 @@ void* sm100_dphl_ptr(void* ws, int B, int N, int D, int M) {
   return (char*)ws + carve100(B, N, D, M, pl).dphl;
 }
 int sm100_J(int N, int D, int M) { return make_plan(N, D, M).J; }
+void* sm100_qhl_ptr(void* ws, int B, int N, int D, int M) {
+  const Plan pl = make_plan(N, D, M);
+  return (char*)ws + carve100(B, N, D, M, pl).qhl;
+}
 
 int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int D, int M, const float* rowmax,
                    const float* rowsum, const float* dP, const float* delta, int ndelta, float* d_cls, void* ws,

@@ -8,12 +8,13 @@ namespace ep {
 bool sm100_supported(int x_dtype, int B, int N, int D, int M);
 size_t sm100_workspace_bytes(int B, int N, int D, int M);
 int sm100_pool_fwd(const void* x, const float* cls, float scale, int B, int N, int D, int M, float* P, float* S,
-                   float* rowmax, float* rowsum, float* attn, int round_p, void* ws, cudaStream_t s);
+                   float* rowmax, float* rowsum, float* attn, int round_p, void* ws, cudaStream_t s, int q_ready = 0);
 int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int D, int M, const float* rowmax,
                    const float* rowsum, const float* dP, const float* delta, int ndelta, float* d_cls, void* ws,
                    cudaStream_t s);
 void* sm100_dphl_ptr(void* ws, int B, int N, int D, int M);   // (B, J, D) bf16 hi/lo rows of dP inside the workspace
 int sm100_J(int N, int D, int M);
+void* sm100_qhl_ptr(void* ws, int B, int N, int D, int M);    // (J, D) bf16 hi/lo rows of the scaled queries
 
 // bf16 tensor map of `rank` dims (dims[0] contiguous; strides in bytes for dims 1..rank-1), 128-byte swizzle,
 // zero fill out of bounds (ep_pool_sm100.cu)

@@ -42,7 +42,8 @@ class EPHeadTrainer:
                  weight_decay: float = 0.0, momentum: float = 0.9, trust_coefficient: float = 0.001,
                  x_dtype: torch.dtype = torch.bfloat16, process_group=None, use_graph: bool = True,
                  overlap_comm: bool = True, optimizer: str = "lars", betas=(0.9, 0.999), eps: float = 1e-8,
-                 accum_iter: int = 1, comm_sms: Optional[int] = None, broadcast_buffers: str = "eval"):
+                 accum_iter: int = 1, comm_sms: Optional[int] = None, broadcast_buffers: str = "eval",
+                 fuse_operands: Optional[bool] = None):
         """comm_sms: SMs left free for the overlapped gradient all-reduce while the token-streaming half of the
         backward pass runs (multi-GPU only; pair it with NCCL_MAX_CTAS <= comm_sms set before the process group is
         created -- bench.py does -- so the collective's CTAs fit there).  None = default_comm_sms(world): measured
@@ -58,6 +59,14 @@ class EPHeadTrainer:
         their own update, so the only observable effect is which statistics evaluation and checkpoints see:
         "eval" (default) broadcasts rank 0's before eval_logits / state export -- same predictions, no per-step
         message; "step" also broadcasts before every training step, as DDP literally does; "off" never."""
+        # fuse_operands (default on; EP_FUSE_OPERANDS=0 turns it off): the bf16 hi/lo operand copies the tcgen05 GEMMs
+        # read are written by the kernels that produce the data -- weights once per step by ep_refresh_operands right
+        # after the optimizer, activations by BatchNorm / cross-entropy / BatchNorm-backward -- instead of by eight
+        # extra launches (the *_ops entry points of include/ep_b200.h).  Same kernels, same operand bits, same results.
+        if fuse_operands is None:
+            fuse_operands = os.environ.get("EP_FUSE_OPERANDS", "1") != "0"
+        self.fuse_ops = bool(fuse_operands)
+        self._ops_key = None                               # parameter versions the weight copies were made from
         if broadcast_buffers not in ("eval", "step", "off"):
             raise ValueError("broadcast_buffers must be 'eval', 'step' or 'off'")
         if optimizer not in ("lars", "adamw", "sgd"):
@@ -136,6 +145,7 @@ class EPHeadTrainer:
         self.hyper = torch.zeros(8, **f32)                 # so rewriting it for the next step cannot race the GPU
         self._write_hyper()
         self.lars_scratch = torch.empty(8192, **f32)       # EP_LARS_SCRATCH_FLOATS
+        self.ce_scratch = torch.zeros(B + 8, **f32)        # per-sample losses + the counter word of ep_ce_fwd_bwd_ops
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
         self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
@@ -163,6 +173,7 @@ class EPHeadTrainer:
         src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
         for t in self.params + self.mus + (self.sq or []) + [self.bn_flat, self.bn.num_batches_tracked]:
             dist.broadcast(t.data, src=src, group=self.group)
+        self.invalidate_operands()
         steps = torch.tensor([self.opt_steps], dtype=torch.int64, device=self.dev)
         dist.broadcast(steps, src=src, group=self.group)
         self.opt_steps = int(steps.item())
@@ -177,21 +188,48 @@ class EPHeadTrainer:
         dist.broadcast(self.bn_flat, src=src, group=self.group)
 
     # ------------------------------------------------------------------ one step, stream-ordered
-    def _forward(self, training: bool):
+    # ------------------------------------------------------------------ operand copies (ABI 2)
+    def invalidate_operands(self):
+        """The weight-derived operand copies are stale: call this after changing a parameter through ``.data`` or a raw
+        pointer (in-place tensor ops, ``load_state_dict`` included, are noticed through the tensors' version counters)."""
+        self._ops_key = None
+
+    def _refresh_launch(self):
+        """ep_refresh_operands on the current stream (captured into the step's graph right after the optimizer)."""
+        pool, fc = self.pool, self.fc
+        _lib.check(self.lib.ep_refresh_operands(pool.cls_token.data_ptr(), pool.v.weight.data_ptr(), float(pool.scale),
+                                                _lib.x_dtype_code(self.x), self.B, self.N, self.D, self.M, self.d_out,
+                                                self.ws.data_ptr(), self.ws.numel(), fc.weight.data_ptr(), self.K,
+                                                self.lin_ws.data_ptr(), self.lin_ws.numel(), _lib.stream_ptr(self.dev)),
+                   "ep_refresh_operands")
+
+    def _ops_check(self):
+        """Make the weight copies current if a parameter changed behind the trainer's back since they were written."""
+        if not self.fuse_ops:
+            return
+        key = tuple((p.data_ptr(), p._version) for p in self.params)
+        if key != self._ops_key:
+            self._refresh_launch()
+            self._ops_key = key
+
+    def _forward(self, training: bool, fp32: bool = False):
         lib, s = self.lib, _lib.stream_ptr(self.dev)
         B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
         pool, bn, fc = self.pool, self.bn, self.fc
-        _lib.check(lib.ep_fwd(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
-                              pool.v.weight.data_ptr(), _lib.ptr(pool.v.bias), float(pool.scale), B, N, D, M, self.d_out,
-                              self.out.data_ptr(), self.S.data_ptr(), self.rowmax.data_ptr(), self.rowsum.data_ptr(),
-                              self.P.data_ptr(), None, self.ws.data_ptr(), self.ws.numel(), s), "ep_fwd")
-        _lib.check(lib.ep_bn_fwd(self.out.data_ptr(), B, Dp, float(bn.eps), float(bn.momentum), int(training),
-                                 bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                                 bn.num_batches_tracked.data_ptr(), self.y.data_ptr(), self.save_mean.data_ptr(),
-                                 self.save_invstd.data_ptr(), s), "ep_bn_fwd")
-        _lib.check(lib.ep_linear_fwd(self.y.data_ptr(), fc.weight.data_ptr(), fc.bias.data_ptr(), B, Dp, K,
-                                     self.logits.data_ptr(), self.lin_ws.data_ptr(), self.lin_ws.numel(), s),
-                   "ep_linear_fwd")
+        Wf, If = (_lib.EP_OPS_WEIGHTS, _lib.EP_OPS_INPUT) if self.fuse_ops else (0, 0)
+        mode = _lib.EP_OPS_FP32 if fp32 else 0                 # evaluation: fp32 contractions, for this call only
+        lin_ws, lin_n = (self.lin_ws.data_ptr(), self.lin_ws.numel())
+        _lib.check(lib.ep_fwd_ops(self._cx.data_ptr(), _lib.x_dtype_code(self._cx), pool.cls_token.data_ptr(),
+                                  pool.v.weight.data_ptr(), _lib.ptr(pool.v.bias), float(pool.scale), B, N, D, M, self.d_out,
+                                  self.out.data_ptr(), self.S.data_ptr(), self.rowmax.data_ptr(), self.rowsum.data_ptr(),
+                                  self.P.data_ptr(), None, self.ws.data_ptr(), self.ws.numel(), Wf | mode, s), "ep_fwd")
+        _lib.check(lib.ep_bn_fwd_ops(self.out.data_ptr(), B, Dp, float(bn.eps), float(bn.momentum), int(training),
+                                     bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                     bn.num_batches_tracked.data_ptr(), self.y.data_ptr(), self.save_mean.data_ptr(),
+                                     self.save_invstd.data_ptr(), K, lin_ws if self.fuse_ops else None, lin_n, mode, s),
+                   "ep_bn_fwd")
+        _lib.check(lib.ep_linear_fwd_ops(self.y.data_ptr(), fc.weight.data_ptr(), fc.bias.data_ptr(), B, Dp, K,
+                                         self.logits.data_ptr(), lin_ws, lin_n, Wf | If | mode, s), "ep_linear_fwd")
 
     # The step in three stream-ordered parts; the gradient exchange sits between them.
     def _part1(self):
@@ -200,28 +238,36 @@ class EPHeadTrainer:
         B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
         pool, fc = self.pool, self.fc
         self._forward(training=True)
-        self.step_loss.zero_()
-        _lib.check(lib.ep_ce_fwd_bwd(self.logits.data_ptr(), self._ct.data_ptr(), B, K, 1.0 / B, 1.0 / B,
-                                     self.step_loss.data_ptr(), self.dlogits.data_ptr(), self.correct.data_ptr(), s),
-                   "ep_ce_fwd_bwd")
+        Wf, If = (_lib.EP_OPS_WEIGHTS, _lib.EP_OPS_INPUT) if self.fuse_ops else (0, 0)
+        lin_ws, lin_n = self.lin_ws.data_ptr(), self.lin_ws.numel()
+        xdt = _lib.x_dtype_code(self._cx)
+        # loss (overwrites step_loss, adds it to the running meter, deterministic), dlogits and -- fused -- their operand copy
+        _lib.check(lib.ep_ce_fwd_bwd_ops(self.logits.data_ptr(), self._ct.data_ptr(), B, K, 1.0 / B, 1.0 / B,
+                                         self.step_loss.data_ptr(), self.loss_sum.data_ptr(), self.dlogits.data_ptr(),
+                                         self.correct.data_ptr(), self.ce_scratch.data_ptr(), Dp,
+                                         lin_ws if self.fuse_ops else None, lin_n, 0, s), "ep_ce_fwd_bwd")
         # classifier gradients: dW/db need only (dlogits, y) and nothing downstream needs them before the
         # exchange, so they run on a side stream (a parallel branch of the captured graph) next to the dy chain
         cur = torch.cuda.current_stream(self.dev)
         self.side_stream.wait_stream(cur)
         with torch.cuda.stream(self.side_stream):
-            _lib.check(lib.ep_linear_bwd(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
-                                         self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), None,
-                                         None, 0, _lib.stream_ptr(self.dev)), "ep_linear_bwd (dW, db)")
-        _lib.check(lib.ep_linear_bwd(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
-                                     None, None, self.dy.data_ptr(),
-                                     self.lin_ws.data_ptr(), self.lin_ws.numel(), s), "ep_linear_bwd (dy)")
-        _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
-                                 self.dout.data_ptr(), s), "ep_bn_bwd")
+            _lib.check(lib.ep_linear_bwd_ops(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
+                                             self.g["fc_w"].data_ptr(), self.g["fc_b"].data_ptr(), None,
+                                             lin_ws if self.fuse_ops else None, lin_n if self.fuse_ops else 0, If,
+                                             _lib.stream_ptr(self.dev)), "ep_linear_bwd (dW, db)")
+        _lib.check(lib.ep_linear_bwd_ops(self.dlogits.data_ptr(), self.y.data_ptr(), fc.weight.data_ptr(), B, Dp, K,
+                                         None, None, self.dy.data_ptr(), lin_ws, lin_n, Wf | If, s), "ep_linear_bwd (dy)")
         d_vb = self.g["v_b"].data_ptr() if pool.v.bias is not None else None
-        _lib.check(lib.ep_bwd_proj(self.dout.data_ptr(), self.P.data_ptr(), self.out.data_ptr(), pool.v.weight.data_ptr(),
-                                   _lib.ptr(pool.v.bias), _lib.x_dtype_code(self._cx),
-                                   B, N, D, M, self.d_out, self.g["v_w"].data_ptr(), d_vb, self.ws.data_ptr(), self.ws.numel(), s),
-                   "ep_bwd_proj")
+        if self.fuse_ops:        # BatchNorm backward + delta and the operand copies of its result for ep_bwd_proj
+            _lib.check(lib.ep_bn_bwd_ops(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
+                                         self.dout.data_ptr(), self.out.data_ptr(), _lib.ptr(pool.v.bias), xdt, N, D, M,
+                                         self.d_out, self.ws.data_ptr(), self.ws.numel(), 0, s), "ep_bn_bwd")
+        else:
+            _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
+                                     self.dout.data_ptr(), s), "ep_bn_bwd")
+        _lib.check(lib.ep_bwd_proj_ops(self.dout.data_ptr(), self.P.data_ptr(), self.out.data_ptr(), pool.v.weight.data_ptr(),
+                                       _lib.ptr(pool.v.bias), xdt, B, N, D, M, self.d_out, self.g["v_w"].data_ptr(), d_vb,
+                                       self.ws.data_ptr(), self.ws.numel(), Wf | If, s), "ep_bwd_proj")
         cur.wait_stream(self.side_stream)
 
     def _part2(self):
@@ -245,10 +291,10 @@ class EPHeadTrainer:
     def _part3(self):
         if self.accum is not None:                         # engine_finetune.py:72-77
             self.accum.add_(self.flat_grad)
-            self.loss_sum.add_(self.step_loss)
             return
         self._apply_optimizer(self.grads)
-        self.loss_sum.add_(self.step_loss)
+        if self.fuse_ops:                                  # operand copies of the updated weights for the next step
+            self._refresh_launch()
 
     def _apply_optimizer(self, grads):
         if self.optimizer == "lars":
@@ -278,6 +324,8 @@ class EPHeadTrainer:
         if self.accum is not None:
             if self.micro % self.accum_iter == 0:          # engine_finetune.py:73-77: step + zero_grad every k-th call
                 self._apply_optimizer(self._accum_grads)
+                if self.fuse_ops:
+                    self._refresh_launch()
                 self.accum.zero_()
                 self.opt_steps += 1
                 if self.optimizer != "lars":
@@ -320,6 +368,7 @@ class EPHeadTrainer:
             if not self.graphs:
                 # one eager step on a side stream first (lazy module loading, NCCL communicator set-up)
                 snap = self._snapshot()
+                self._ops_check()
                 side = torch.cuda.Stream(device=self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
                 with torch.cuda.stream(side):
@@ -345,6 +394,7 @@ class EPHeadTrainer:
 
     def _run(self):
         if not self.use_graph:
+            self._ops_check()
             if self.launches_per_step is None:
                 n0 = self.lib.ep_launch_count()
                 self._step_body()
@@ -353,6 +403,7 @@ class EPHeadTrainer:
                 self._step_body()
             return
         graphs = self._ensure_graphs()
+        self._ops_check()                                   # (after the capture's warm-up step has been rolled back)
         if len(graphs) == 1:
             graphs[0].replay()
         else:
@@ -373,6 +424,7 @@ class EPHeadTrainer:
             return
         self._cx, self._ct = self._registered[key]
         self._ensure_graphs()
+        self._ops_check()
 
     def _snapshot(self):
         bn = self.bn
@@ -512,11 +564,8 @@ class EPHeadTrainer:
         self.x[:b].copy_(x, non_blocking=True)
         if b < self.B:
             self.x[b:].zero_()                # samples are independent in eval mode: the padding rows are dropped below
-        self.lib.ep_set_gemm_mode(1)          # evaluation: fp32 contractions, predictions must not move
-        try:
-            self._forward(training=False)
-        finally:
-            self.lib.ep_set_gemm_mode(0)
+        self._ops_check()
+        self._forward(training=False, fp32=True)   # evaluation: fp32 contractions (per call), predictions must not move
         return self.logits[:b].clone()
 
     def mean_loss(self) -> float:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EP_ABI_VERSION 1
+#define EP_ABI_VERSION 2
 
 #define EP_DTYPE_BF16 0
 #define EP_DTYPE_F32  1
@@ -198,6 +198,65 @@ int ep_ce_fwd_bwd(const float* logits, const long long* targets, int B, int K, f
 int ep_lars_step(int n, float* const* params_host, const float* const* grads_host, float* const* mus_host,
                  const long long* numels_host, const int* apply_trust_host, const float* hyper,
                  float* scratch, void* stream);
+
+/* ---- Operand reuse across the calls of one training step (ABI 2) --------------------------------------------
+ * The tcgen05 GEMMs of the head read their fp32 operands as bf16 hi/lo copies (3-term products).  Every entry point
+ * above is self-contained: it derives the copies it needs from its fp32 arguments, which costs eight small launches
+ * per training step.  The *_ops variants below take an `ops` bitmask instead and let the kernel that PRODUCES a tensor
+ * write the operand copy its consumer reads, into the same caller-owned workspaces (`workspace` of
+ * ep_workspace_bytes(), `lin_workspace` of ep_linear_workspace_bytes(); their layout is private to the library):
+ *   EP_OPS_WEIGHTS  the weight-derived copies (scaled queries, v.weight, fc.weight, both orientations) in the
+ *                   workspaces are current: ep_refresh_operands() has run on them since the parameters last changed
+ *                   (a training loop calls it once per step, right after the optimizer);
+ *   EP_OPS_INPUT    the activation-derived copies were written by the producing *_ops call of this step:
+ *                   ep_bn_fwd_ops -> y for ep_linear_fwd_ops / the dW of ep_linear_bwd_ops; ep_ce_fwd_bwd_ops ->
+ *                   dlogits for ep_linear_bwd_ops; ep_bn_bwd_ops -> g_out copies and delta for ep_bwd_proj_ops;
+ *   EP_OPS_FP32     this call runs its contractions as fp32 FMAs on the CUDA cores (what ep_set_gemm_mode(1) selects
+ *                   process-wide, here per call and per thread: evaluation next to training on another stream).
+ * A flag is a promise by the caller; with ops == 0 a *_ops call behaves exactly like the plain one.  Where a shape is
+ * outside what the copies cover (bf16 rows need F % 8 == 0, K % 8 == 0, c % 4 == 0) producers and consumers fall
+ * back to self-made copies by the same rule, so the flags are always safe to pass.  Results are identical either
+ * way (same kernels, same operand bits); ep_linear_bwd_ops with EP_OPS_INPUT also moves the classifier weight
+ * gradient from the mma.sync TF32 kernel to the tcgen05 3-term GEMM (4e-6 instead of 3e-4 relative error). */
+#define EP_OPS_WEIGHTS 1
+#define EP_OPS_INPUT   2
+#define EP_OPS_FP32    4
+/* Writes every weight-derived operand copy: scale * cls_token as bf16 hi/lo rows, v.weight as [hi|hi|lo] rows and
+ * as per-query transposed [hi|hi|lo] rows, fc.weight (K, F = D / d_out) as [hi|hi|lo] rows and transposed.  One
+ * launch.  fc_w / lin_workspace may be NULL (pooling head only). */
+int ep_refresh_operands(const float* cls_token, const float* v_w, float scale, int x_dtype, int B, int N, int D, int M,
+                        int d_out, void* workspace, size_t workspace_bytes, const float* fc_w, int K,
+                        void* lin_workspace, size_t lin_workspace_bytes, void* stream);
+int ep_fwd_ops(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
+               float scale, int B, int N, int D, int M, int d_out,
+               float* out, float* S, float* rowmax, float* rowsum, float* P, float* attn,
+               void* workspace, size_t workspace_bytes, int ops, void* stream);
+int ep_bwd_proj_ops(const float* g_out, const float* P, const float* out, const float* v_w, const float* v_b, int x_dtype,
+                    int B, int N, int D, int M, int d_out, float* d_v_w, float* d_v_b,
+                    void* workspace, size_t workspace_bytes, int ops, void* stream);
+/* ep_bn_fwd + the operand copy of y for a Linear(F, K) that follows (lin_workspace of
+ * ep_linear_workspace_bytes(B, F, K); NULL = plain ep_bn_fwd). */
+int ep_bn_fwd_ops(const float* h, int B, int F, float eps, float momentum, int training,
+                  float* running_mean, float* running_var, long long* num_batches_tracked,
+                  float* y, float* save_mean, float* save_invstd, int K, void* lin_workspace, size_t lin_workspace_bytes,
+                  int ops, void* stream);
+/* ep_bn_bwd where dh is the g_out of ep_bwd_proj_ops: also leaves in `workspace` the operand copies of dh and
+ * delta = dh . (out - v_b) per (sample, query) -- `out`, `v_b` as in ep_bwd. */
+int ep_bn_bwd_ops(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh,
+                  const float* out, const float* v_b, int x_dtype, int N, int D, int M, int d_out,
+                  void* workspace, size_t workspace_bytes, int ops, void* stream);
+int ep_linear_fwd_ops(const float* y, const float* W, const float* b, int B, int F, int K, float* logits,
+                      void* lin_workspace, size_t lin_workspace_bytes, int ops, void* stream);
+int ep_linear_bwd_ops(const float* dlogits, const float* y, const float* W, int B, int F, int K,
+                      float* dW, float* db, float* dy, void* lin_workspace, size_t lin_workspace_bytes, int ops,
+                      void* stream);
+/* ep_ce_fwd_bwd with a deterministic loss and no zeroing by the caller: step_loss[0] = sum_b nll_b * loss_scale is
+ * OVERWRITTEN (rows summed in a fixed order by the last CTA to finish), loss_acc[0] += that value when non-NULL (a
+ * running meter).  scratch: B + 1 floats; word B is a counter that must be 0 before the first call and is left 0.
+ * With lin_workspace (and F of the Linear(F, K) whose backward follows) the operand copy of dlogits is written too. */
+int ep_ce_fwd_bwd_ops(const float* logits, const long long* targets, int B, int K, float loss_scale, float grad_scale,
+                      float* step_loss, float* loss_acc, float* dlogits, int* correct, float* scratch,
+                      int F, void* lin_workspace, size_t lin_workspace_bytes, int ops, void* stream);
 
 /* The other two optimizers main_linprobe.py:403-408 can build ({"lars": LARS, "adamw": AdamW}, else SGD), one
  * launch for all tensors; pointer tables are HOST arrays of device pointers, hyper is a DEVICE array.

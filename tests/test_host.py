@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in ep_b200.h but not exported"
     assert declared == set(E._lib.EXPORTED_SYMBOLS), declared ^ set(E._lib.EXPORTED_SYMBOLS)
     L = E._lib.load()
-    assert L.ep_abi_version() == 1
+    assert L.ep_abi_version() == 2
     assert b"NULL" in L.ep_strerror(-1)
 
 

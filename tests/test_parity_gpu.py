@@ -408,3 +408,48 @@ def test_accum_iter_matches_large_batch_gradient():
     opt.step()
     for (k, a), (_, b) in zip(h_acc.named_parameters(), h_ref.named_parameters()):
         close(a.detach(), b.detach(), 1e-3, "accum " + k)
+
+
+FUSE_CASES = [
+    # B, N, D, M, K, d_out, bias   (B % 64 == 0: hi/lo P and every tcgen05 GEMM; the others exercise the fall-backs)
+    (64, 70, 256, 8, 40, 1, 0),          # c = 32: bf16 copies everywhere
+    (128, 33, 1152, 32, 1000, 1, 0),     # c = 36: tf32 copies of g / W_m^T, bf16 for the rest (config 3's head)
+    (64, 40, 256, 8, 24, 2, 1),          # d_out = 2 with bias: delta subtracts the bias
+    (20, 17, 128, 8, 10, 1, 0),          # B % 64 != 0: fp32 P, mma.sync weight gradient, g^T copy unused
+    (64, 50, 256, 4, 36, 1, 0),          # K % 8 != 0: classifier copies fall back to the self-made ones
+]
+
+
+@pytest.mark.parametrize("case", FUSE_CASES, ids=lambda c: "B%d_N%d_D%d_M%d_K%d_do%d_b%d" % c)
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_operand_copies_by_producers_match_self_contained_calls(case, graph):
+    """ABI 2 (*_ops entry points): operand copies written by the producing kernels + ep_refresh_operands give the
+    step the self-contained calls give -- the same operand bits reach the same GEMMs.  Only the classifier weight
+    gradient changes kernel (tcgen05 3-term instead of mma.sync TF32: closer to the oracle, compared at 1e-3)."""
+    B, N, D, M, K, d_out, bias = case
+    p = O.build_head(D, M, K, seed=3, d_out=d_out, qkv_bias=bool(bias))
+    p.cls_token = p.cls_token * 8.0
+    h_f, h_s = head_from_params(p, K), head_from_params(p, K)
+    t_f = E.EPHeadTrainer(h_f, B, N, lr=0.3, weight_decay=1e-4, use_graph=graph, fuse_operands=True)
+    t_s = E.EPHeadTrainer(h_s, B, N, lr=0.3, weight_decay=1e-4, use_graph=graph, fuse_operands=False)
+    for it in range(3):
+        x = O.synthetic_tokens(B, N, D, seed=300 + it).to(DEV)
+        y = O.synthetic_labels(B, K, seed=310 + it).to(DEV)
+        if it == 2:                       # a parameter changed behind the trainers' back: the copies must follow
+            with torch.no_grad():
+                for h in (h_f, h_s):
+                    h[0].cls_token.mul_(1.25)
+                    h[2].weight.add_(0.01)
+        t_f.train_step(x, y)
+        t_s.train_step(x, y)
+        torch.cuda.synchronize()
+        assert abs(float(t_f.step_loss) - float(t_s.step_loss)) <= 2e-6 * abs(float(t_s.step_loss)), it
+        for k in ("cls", "v_w", "fc_b"):
+            close(t_f.g[k], t_s.g[k], 2e-5, f"step {it} grad {k}")
+        close(t_f.g["fc_w"], t_s.g["fc_w"], 1e-3, f"step {it} grad fc_w")
+        close(t_f.logits, t_s.logits, 1e-6, f"step {it} logits")
+    assert t_f.launches_per_step < t_s.launches_per_step
+    assert abs(t_f.mean_loss() - t_s.mean_loss()) <= 1e-5 * abs(t_s.mean_loss())
+    xe = O.synthetic_tokens(B - 3 if B > 8 else B, N, D, seed=399).to(DEV)
+    assert torch.equal(t_f.eval_logits(xe).argmax(1), t_s.eval_logits(xe).argmax(1))
+    close(t_f.eval_logits(xe), t_s.eval_logits(xe), 1e-5, "eval logits")
