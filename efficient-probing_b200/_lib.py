@@ -73,7 +73,7 @@ _SIGNATURES = {
     "ep_ce_fwd_bwd_ops": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
 }
-EP_OPS_WEIGHTS, EP_OPS_INPUT, EP_OPS_FP32 = 1, 2, 4
+EP_OPS_WEIGHTS, EP_OPS_INPUT, EP_OPS_FP32, EP_OPS_NO_DW, EP_OPS_ONLY_DW = 1, 2, 4, 8, 16
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 

@@ -267,12 +267,17 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
   // delta[b, m] = sum_n A dA = dP[b, m] . P[b, m] = g[b, m, :] . (out[b, m, :] - bias[m, :])
   // (EP_OPS_INPUT: ep_bn_bwd_ops left delta and the copies of g_out in the workspace -- g_ops_kernel, ep_ops.cu)
   const bool g_ready = (ops & EP_OPS_INPUT) != 0, w_ready = (ops & EP_OPS_WEIGHTS) != 0;
-  if (!g_ready && (rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
+  // the weight-gradient half and the dP half are independent: EP_OPS_ONLY_DW / EP_OPS_NO_DW let a caller run them
+  // as two calls on two streams (134 MB of P read next to 134 MB of dP written)
+  const bool do_dw = !(ops & EP_OPS_NO_DW), do_dp = !(ops & EP_OPS_ONLY_DW);
+  if ((ops & EP_OPS_NO_DW) && (ops & EP_OPS_ONLY_DW)) return EP_ERR_SHAPE;
+  if (!g_ready && do_dp && (rc = launch_delta_from_out(g_out, out, v_b, (long long)B * M, M, c, delta, s))) return rc;
   const bool hilo = p_layout < 0 ? p_hilo(x_dtype, B, N, D, M, d_out) : p_layout == 1;
   if (hilo && !(use_tc() && c % 4 == 0 && B % 64 == 0 && D % 64 == 0)) return EP_ERR_UNSUPPORTED;   // mode changed since ep_fwd
   if (use_tc() && c % 4 == 0) {
     // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]: contraction over the batch
-    if (hilo) {
+    if (!do_dw) {
+    } else if (hilo) {
       // tcgen05 3-term bf16 GEMM: rows d, cols j, contraction over b.  A = P's hi/lo rows in place, MN-major
       // (channels contiguous); B = g^T as [g_hi | g_hi | g_lo] (K-major copy, 6*B*D' bytes)
       void* g3t = (char*)workspace + w.g_t;
@@ -291,8 +296,8 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
       if ((rc = launch_gemm_tn(g_out, P, d_v_w, c, D, B, M, Dp, (long long)M * D, D, c, D, (long long)c * D, s))) return rc;
       tm.mark("dW tn-gemm");
     }
-    if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
-    {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05, 3xTF32 (dP drives the query gradient)
+    if (do_dw && d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
+    if (do_dp) {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]: tcgen05, 3xTF32 (dP drives the query gradient)
       float* g3 = (float*)((char*)workspace + w.g_r);              // [(b, m)][3c]  = [big | small | big]
       float* w3 = (float*)((char*)workspace + w.w_t);              // [m][d][3c]    = [big | big | small]
       const int bf = kSplitBf16 && c % 8 == 0;               // bf16 rows need 16-byte strides: 3c * 2 B
@@ -320,7 +325,7 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
     }
     return 0;
   }
-  {  // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]
+  if (do_dw) {  // d_v_w[m*c + j, d] = sum_b g[b, m*c + j] * P[b, m, d]
     GemmDesc g{};
     g.A = g_out; g.B = P; g.C = d_v_w;
     g.I = c; g.J = D; g.K = B; g.Z = M;
@@ -329,8 +334,8 @@ int bwd_proj_impl(const float* g_out, const float* P, int p_layout, int general_
     g.c_i = D; g.c_j = 1; g.c_z = (long long)c * D;
     if ((rc = launch_gemm_v0(g, s))) return rc;
   }
-  if (d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
-  {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]
+  if (do_dw && d_v_b && (rc = launch_colsum(g_out, B, Dp, d_v_b, s))) return rc;
+  if (do_dp) {  // dP[b, m, d] = sum_j g[b, m*c + j] * v_w[m*c + j, d]
     GemmDesc g{};
     g.A = g_out; g.B = v_w; g.C = dP;
     g.I = B; g.J = D; g.K = c; g.Z = M;

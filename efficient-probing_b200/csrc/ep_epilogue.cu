@@ -7,7 +7,7 @@ namespace ep {
 // ---------------- BatchNorm1d(affine=False, eps) -- probe_heads.py:109-110 ----------------
 // one CTA per 8 features (a 32-byte sector per row), 8 x 128 threads: x = feature, y strides the batch.
 // F/8 CTAs instead of F/32 keep 128 SMs busy at F = 1024; a warp still reads whole sectors.
-constexpr int BN_F = 8, BN_Y = 128;
+constexpr int BN_F = 8, BN_Y = 128, BN_CACHE = 8;
 __device__ __forceinline__ float block_colsum(float v, float (*red)[BN_F + 1]) {
   red[threadIdx.y][threadIdx.x] = v;
   __syncthreads();
@@ -31,12 +31,28 @@ bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float moment
   const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
   float mean, invstd;
+  // a thread's rows stay in registers between the passes when the batch is small enough (B <= 1024: one load, not three)
+  const bool cached = B <= BN_Y * BN_CACHE;
+  float hv[BN_CACHE];
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < BN_CACHE; ++i) {
+      const int b = threadIdx.y + i * BN_Y;
+      hv[i] = (ok && b < B) ? h[(size_t)b * F + f] : 0.f;
+    }
+  }
   if (training) {
     float s = 0.f;
-    if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) s += h[(size_t)b * F + f];
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < BN_CACHE; ++i) if (threadIdx.y + i * BN_Y < B) s += hv[i];
+    } else if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) s += h[(size_t)b * F + f];
     mean = block_colsum(s, red) / B;
     float v = 0.f;
-    if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) { const float d = h[(size_t)b * F + f] - mean; v = fmaf(d, d, v); }
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < BN_CACHE; ++i) if (threadIdx.y + i * BN_Y < B) { const float d = hv[i] - mean; v = fmaf(d, d, v); }
+    } else if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) { const float d = h[(size_t)b * F + f] - mean; v = fmaf(d, d, v); }
     const float var = block_colsum(v, red) / B;                    // biased, used to normalise
     invstd = rsqrtf(var + eps);
     if (ok && threadIdx.y == 0) {
@@ -51,13 +67,21 @@ bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float moment
     mean = ok ? running_mean[f] : 0.f;
     invstd = ok ? 1.f / sqrtf(running_var[f] + eps) : 0.f;
   }
-  if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) {
-    const float v = (h[(size_t)b * F + f] - mean) * invstd;
+  auto emit = [&](int b, float hval) {
+    const float v = (hval - mean) * invstd;
     y[(size_t)b * F + f] = v;
     if (y3) {
       const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
       __nv_bfloat16* r = y3 + (size_t)b * 3 * Fp + f;
       r[0] = hi; r[Fp] = lo; r[2 * Fp] = hi;
+    }
+  };
+  if (ok) {
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < BN_CACHE; ++i) if (threadIdx.y + i * BN_Y < B) emit(threadIdx.y + i * BN_Y, hv[i]);
+    } else {
+      for (int b = threadIdx.y; b < B; b += BN_Y) emit(b, h[(size_t)b * F + f]);
     }
   } else if (y3 && f < Fp) for (int b = threadIdx.y; b < B; b += BN_Y) {
     __nv_bfloat16* r = y3 + (size_t)b * 3 * Fp + f;
@@ -73,7 +97,19 @@ bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const f
   const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
   float s1 = 0.f, s2 = 0.f;
-  if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) {
+  const bool cached = B <= BN_Y * BN_CACHE;                        // rows of this thread kept in registers
+  float gv[BN_CACHE], yv[BN_CACHE];
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < BN_CACHE; ++i) {
+      const int b = threadIdx.y + i * BN_Y;
+      const bool in = ok && b < B;
+      gv[i] = in ? dy[(size_t)b * F + f] : 0.f;
+      yv[i] = in ? y[(size_t)b * F + f] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < BN_CACHE; ++i) if (threadIdx.y + i * BN_Y < B) { s1 += gv[i]; s2 = fmaf(gv[i], yv[i], s2); }
+  } else if (ok) for (int b = threadIdx.y; b < B; b += BN_Y) {
     const float g = dy[(size_t)b * F + f];
     s1 += g;
     s2 = fmaf(g, y[(size_t)b * F + f], s2);
@@ -82,12 +118,21 @@ bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const f
   const float m2 = block_colsum(s2, red) / B;
   if (ok) {
     const float is = invstd[f];
-    for (int b = threadIdx.y; b < B; b += BN_Y)
-      dh[(size_t)b * F + f] = is * (dy[(size_t)b * F + f] - m1 - y[(size_t)b * F + f] * m2);
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < BN_CACHE; ++i) {
+        const int b = threadIdx.y + i * BN_Y;
+        if (b < B) dh[(size_t)b * F + f] = is * (gv[i] - m1 - yv[i] * m2);
+      }
+    } else {
+      for (int b = threadIdx.y; b < B; b += BN_Y)
+        dh[(size_t)b * F + f] = is * (dy[(size_t)b * F + f] - m1 - y[(size_t)b * F + f] * m2);
+    }
   }
 }
 
 // ---------------- CrossEntropyLoss (mean) fwd+bwd, one CTA per row ----------------
+constexpr int CE_CACHE = 4;
 __global__ void __launch_bounds__(256)
 ce_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, int K, float loss_scale,
           float grad_scale, float* loss_sum, float* __restrict__ dlogits, int* correct,
@@ -99,11 +144,23 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target
   __shared__ int redi[8];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* row = logits + (size_t)b * K;
+  // the row stays in registers between the passes when K <= 1024 (4 values per thread: one load, one exp per element)
+  const bool cached = K <= 256 * CE_CACHE;
+  float rv[CE_CACHE];
   float mx = -INFINITY;
   int arg = 0x7fffffff;
-  for (int k = threadIdx.x; k < K; k += 256) {
-    const float v = row[k];
-    if (v > mx) { mx = v; arg = k; }
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < CE_CACHE; ++i) {
+      const int k = threadIdx.x + i * 256;
+      rv[i] = k < K ? row[k] : -INFINITY;
+      if (rv[i] > mx) { mx = rv[i]; arg = k; }
+    }
+  } else {
+    for (int k = threadIdx.x; k < K; k += 256) {
+      const float v = row[k];
+      if (v > mx) { mx = v; arg = k; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -119,7 +176,15 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target
     if (redf[w] > mx || (redf[w] == mx && redi[w] < arg)) { mx = redf[w]; arg = redi[w]; }
   __syncthreads();
   float s = 0.f;
-  for (int k = threadIdx.x; k < K; k += 256) s += expf(row[k] - mx);
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < CE_CACHE; ++i) {
+      rv[i] = threadIdx.x + i * 256 < K ? expf(rv[i] - mx) : 0.f;      // from here on: exp(logit - max)
+      s += rv[i];
+    }
+  } else {
+    for (int k = threadIdx.x; k < K; k += 256) s += expf(row[k] - mx);
+  }
   s = warp_sum(s);
   if (lane == 0) redf[warp] = s;
   __syncthreads();
@@ -128,16 +193,24 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target
   for (int w = 0; w < 8; ++w) s += redf[w];
   const int t = (int)targets[b];
   const float inv = 1.f / s;
-  if (dlogits)
-    for (int k = threadIdx.x; k < (d3 ? Kp : K); k += 256) {
-      const float v = k < K ? (expf(row[k] - mx) * inv - (k == t ? 1.f : 0.f)) * grad_scale : 0.f;
-      if (k < K) dlogits[(size_t)b * K + k] = v;
-      if (d3) {
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        __nv_bfloat16* r = d3 + (size_t)b * 3 * Kp + k;
-        r[0] = hi; r[Kp] = lo; r[2 * Kp] = hi;
-      }
+  auto emit = [&](int k, float e) {                                  // e = exp(logit - max), 0 in the padding
+    const float v = k < K ? (e * inv - (k == t ? 1.f : 0.f)) * grad_scale : 0.f;
+    if (k < K) dlogits[(size_t)b * K + k] = v;
+    if (d3) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* r = d3 + (size_t)b * 3 * Kp + k;
+      r[0] = hi; r[Kp] = lo; r[2 * Kp] = hi;
     }
+  };
+  if (dlogits) {
+    const int kend = d3 ? Kp : K;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < CE_CACHE; ++i) if (threadIdx.x + i * 256 < kend) emit(threadIdx.x + i * 256, rv[i]);
+    } else {
+      for (int k = threadIdx.x; k < kend; k += 256) emit(k, k < K ? expf(row[k] - mx) : 0.f);
+    }
+  }
   const float nll = (logf(s) + mx - row[t]) * loss_scale;
   if (!scratch) {
     if (threadIdx.x == 0) {
@@ -185,12 +258,26 @@ struct LarsArgs {
 // hyper = {lr, weight_decay, momentum, trust_coefficient, grad_scale}
 
 // deterministic norms: every CTA writes its partial sums, the update kernel adds them in a fixed order
-__global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float* __restrict__ hyper, float* partial) {
+__global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float* __restrict__ hyper, float* partial, int vec) {
   const int t = blockIdx.y;
   if (!a.trust[t]) return;
   const float wd = hyper[1], gs = hyper[4];
   float sp = 0.f, su = 0.f;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
+  // vec: every tensor is 16-byte aligned -- 128-bit loads for the bulk, the last n % 4 elements one by one
+  const long long n4 = vec ? a.n[t] >> 2 : 0;
+  const float4* p4 = reinterpret_cast<const float4*>(a.p[t]);
+  const float4* g4 = reinterpret_cast<const float4*>(a.g[t]);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 p = p4[i], g = g4[i];
+    const float pv[4] = {p.x, p.y, p.z, p.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float u = fmaf(wd, pv[e], gv[e] * gs);
+      sp = fmaf(pv[e], pv[e], sp);
+      su = fmaf(u, u, su);
+    }
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
     const float p = a.p[t][i];
     const float u = fmaf(wd, p, a.g[t][i] * gs);
     sp = fmaf(p, p, sp);
@@ -210,7 +297,7 @@ __global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float*
 }
 
 __global__ void __launch_bounds__(256) lars_update_kernel(LarsArgs a, const float* __restrict__ hyper,
-                                                          const float* __restrict__ partial) {
+                                                          const float* __restrict__ partial, int vec) {
   const int t = blockIdx.y;
   const float lr = hyper[0], wd = hyper[1], mom = hyper[2], tc = hyper[3], gs = hyper[4];
   __shared__ float qs;
@@ -231,7 +318,25 @@ __global__ void __launch_bounds__(256) lars_update_kernel(LarsArgs a, const floa
   }
   __syncthreads();
   const float q = qs;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
+  const long long n4 = vec ? a.n[t] >> 2 : 0;
+  float4* p4 = reinterpret_cast<float4*>(a.p[t]);
+  float4* m4 = reinterpret_cast<float4*>(a.mu[t]);
+  const float4* g4 = reinterpret_cast<const float4*>(a.g[t]);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 p = p4[i], g = g4[i], mu = m4[i];
+    float pv[4] = {p.x, p.y, p.z, p.w}, mv[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float u = gv[e] * gs;
+      if (tr) u = fmaf(wd, pv[e], u) * q;
+      mv[e] = fmaf(mom, mv[e], u);
+      pv[e] = fmaf(-lr, mv[e], pv[e]);
+    }
+    m4[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    p4[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * 256) {
     const float p = a.p[t][i];
     float u = a.g[t][i] * gs;
     if (tr) u = fmaf(wd, p, u) * q;
@@ -386,18 +491,20 @@ extern "C" int ep_lars_step(int n, float* const* params, const float* const* gra
   LarsArgs a;
   a.count = n;
   long long mx = 0;
+  int vec = 1;
   for (int i = 0; i < n; ++i) {
     if (!params[i] || !grads[i] || !mus[i]) return EP_ERR_NULL;
     a.p[i] = params[i]; a.g[i] = grads[i]; a.mu[i] = mus[i]; a.n[i] = numels[i]; a.trust[i] = apply_trust[i];
     if (numels[i] > mx) mx = numels[i];
+    if ((reinterpret_cast<uintptr_t>(params[i]) | reinterpret_cast<uintptr_t>(grads[i]) | reinterpret_cast<uintptr_t>(mus[i])) & 15) vec = 0;
   }
   cudaStream_t s = (cudaStream_t)stream;
   int bx = (int)((mx + 256 * 8 - 1) / (256 * 8));
   if (bx < 1) bx = 1;
   if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;                  // 2 * n * bx <= EP_LARS_SCRATCH_FLOATS
-  lars_norm_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch);
+  lars_norm_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch, vec);
   EP_LAUNCH_CHECK();
-  lars_update_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch);
+  lars_update_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch, vec);
   EP_LAUNCH_CHECK();
   return 0;
 }

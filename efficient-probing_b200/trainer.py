@@ -67,6 +67,7 @@ class EPHeadTrainer:
             fuse_operands = os.environ.get("EP_FUSE_OPERANDS", "1") != "0"
         self.fuse_ops = bool(fuse_operands)
         self._ops_key = None                               # parameter versions the weight copies were made from
+        self.parallel_dw = os.environ.get("EP_PARALLEL_DW", "1") != "0"
         if broadcast_buffers not in ("eval", "step", "off"):
             raise ValueError("broadcast_buffers must be 'eval', 'step' or 'off'")
         if optimizer not in ("lars", "adamw", "sgd"):
@@ -265,9 +266,20 @@ class EPHeadTrainer:
         else:
             _lib.check(lib.ep_bn_bwd(self.dy.data_ptr(), self.y.data_ptr(), self.save_invstd.data_ptr(), B, Dp,
                                      self.dout.data_ptr(), s), "ep_bn_bwd")
-        _lib.check(lib.ep_bwd_proj_ops(self.dout.data_ptr(), self.P.data_ptr(), self.out.data_ptr(), pool.v.weight.data_ptr(),
-                                       _lib.ptr(pool.v.bias), xdt, B, N, D, M, self.d_out, self.g["v_w"].data_ptr(), d_vb,
-                                       self.ws.data_ptr(), self.ws.numel(), Wf | If, s), "ep_bwd_proj")
+        def bwd_proj(ops, stream):
+            _lib.check(lib.ep_bwd_proj_ops(self.dout.data_ptr(), self.P.data_ptr(), self.out.data_ptr(),
+                                           pool.v.weight.data_ptr(), _lib.ptr(pool.v.bias), xdt, B, N, D, M, self.d_out,
+                                           self.g["v_w"].data_ptr(), d_vb, self.ws.data_ptr(), self.ws.numel(), ops, stream),
+                       "ep_bwd_proj")
+        if self.fuse_ops and self.parallel_dw:
+            # d v.weight (reads the 134 MB of P) is not needed before the exchange / the optimizer: it joins the classifier
+            # gradients on the side branch and runs next to dP (134 MB written) instead of in front of it
+            self.side_stream.wait_stream(cur)
+            with torch.cuda.stream(self.side_stream):
+                bwd_proj(Wf | If | _lib.EP_OPS_ONLY_DW, _lib.stream_ptr(self.dev))
+            bwd_proj(Wf | If | _lib.EP_OPS_NO_DW, s)
+        else:
+            bwd_proj(Wf | If, s)
         cur.wait_stream(self.side_stream)
 
     def _part2(self):

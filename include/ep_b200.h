@@ -221,6 +221,11 @@ int ep_lars_step(int n, float* const* params_host, const float* const* grads_hos
 #define EP_OPS_WEIGHTS 1
 #define EP_OPS_INPUT   2
 #define EP_OPS_FP32    4
+/* ep_bwd_proj_ops only: run one half of the call -- everything but d_v_w / d_v_b (NO_DW: delta and dP, what
+ * ep_bwd_pool needs), or d_v_w / d_v_b alone (ONLY_DW).  The halves are independent, so a caller can issue them on two
+ * streams (the weight gradient is not needed before the optimizer / the gradient exchange). */
+#define EP_OPS_NO_DW   8
+#define EP_OPS_ONLY_DW 16
 /* Writes every weight-derived operand copy: scale * cls_token as bf16 hi/lo rows, v.weight as [hi|hi|lo] rows and
  * as per-query transposed [hi|hi|lo] rows, fc.weight (K, F = D / d_out) as [hi|hi|lo] rows and transposed.  One
  * launch.  fc_w / lin_workspace may be NULL (pooling head only). */

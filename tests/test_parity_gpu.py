@@ -443,13 +443,14 @@ def test_operand_copies_by_producers_match_self_contained_calls(case, graph):
         t_f.train_step(x, y)
         t_s.train_step(x, y)
         torch.cuda.synchronize()
-        assert abs(float(t_f.step_loss) - float(t_s.step_loss)) <= 2e-6 * abs(float(t_s.step_loss)), it
+        assert abs(float(t_f.step_loss) - float(t_s.step_loss)) <= (2e-6 if it == 0 else 1e-4) * abs(float(t_s.step_loss)), it
         for k in ("cls", "v_w", "fc_b"):
-            close(t_f.g[k], t_s.g[k], 2e-5, f"step {it} grad {k}")
+            close(t_f.g[k], t_s.g[k], 2e-5 if it == 0 else 1e-3, f"step {it} grad {k}")
         close(t_f.g["fc_w"], t_s.g["fc_w"], 1e-3, f"step {it} grad fc_w")
-        close(t_f.logits, t_s.logits, 1e-6, f"step {it} logits")
+        # (from the second step on the parameters differ by what the two classifier weight-gradient kernels differ)
+        close(t_f.logits, t_s.logits, 2e-6 if it == 0 else 1e-4, f"step {it} logits")
     assert t_f.launches_per_step < t_s.launches_per_step
-    assert abs(t_f.mean_loss() - t_s.mean_loss()) <= 1e-5 * abs(t_s.mean_loss())
+    assert abs(t_f.mean_loss() - t_s.mean_loss()) <= 1e-4 * abs(t_s.mean_loss())
     xe = O.synthetic_tokens(B - 3 if B > 8 else B, N, D, seed=399).to(DEV)
     assert torch.equal(t_f.eval_logits(xe).argmax(1), t_s.eval_logits(xe).argmax(1))
-    close(t_f.eval_logits(xe), t_s.eval_logits(xe), 1e-5, "eval logits")
+    close(t_f.eval_logits(xe), t_s.eval_logits(xe), 1e-3, "eval logits")
