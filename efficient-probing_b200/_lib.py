@@ -58,7 +58,7 @@ _SIGNATURES = {
     "ep_lars_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     # ABI 2: operand copies written by their producers (the *_ops variants; trailing `ops` bitmask)
     "ep_refresh_operands": (c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p, c_int,
-                                                                                  c_void_p, c_size_t, c_void_p]),
+                                                                                  c_void_p, c_size_t, c_int, c_void_p]),
     "ep_fwd_ops": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 5 +
                    [c_void_p] * 6 + [c_void_p, c_size_t, c_int, c_void_p]),
     "ep_bwd_proj_ops": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

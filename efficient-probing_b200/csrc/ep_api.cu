@@ -626,7 +626,8 @@ extern "C" int ep_bn_bwd_ops(const float* dy, const float* y, const float* save_
 
 extern "C" int ep_refresh_operands(const float* cls_token, const float* v_w, float scale, int x_dtype, int B, int N, int D,
                                    int M, int d_out, void* workspace, size_t workspace_bytes, const float* fc_w, int K,
-                                   void* lin_workspace, size_t lin_workspace_bytes, void* stream) {
+                                   void* lin_workspace, size_t lin_workspace_bytes, int which, void* stream) {
+  if (which == 0) which = EP_REFRESH_ALL;
   if (!cls_token || !v_w) return EP_ERR_NULL;
   if (B <= 0 || N <= 0 || D <= 0 || M <= 0 || d_out <= 0 || D % (d_out * M) != 0) return EP_ERR_SHAPE;
   const Ws w = carve(B, N, D, M);
@@ -634,19 +635,19 @@ extern "C" int ep_refresh_operands(const float* cls_token, const float* v_w, flo
   const int Dp = D / d_out, c = Dp / M;
   RefreshJob jobs[kMaxRefreshJobs];
   int n = 0, rc = 0;
-  if (use_sm100(x_dtype, B, N, D, M, &rc)) {           // scaled queries as hi/lo rows (one-pass forward, logit kernels)
+  if ((which & EP_REFRESH_QUERIES) && use_sm100(x_dtype, B, N, D, M, &rc)) {           // scaled queries as hi/lo rows (one-pass forward, logit kernels)
     RefreshJob j{};
     j.type = REFRESH_HILO; j.src = cls_token; j.dst = sm100_qhl_ptr((char*)workspace + w.sm100, B, N, D, M);
     j.scale = scale; j.M = M; j.J = sm100_J(N, D, M); j.D = D;
     jobs[n++] = j;
   }
-  if (p_hilo(x_dtype, B, N, D, M, d_out)) {            // projection: [hi | hi | lo] rows of v.weight
+  if ((which & EP_REFRESH_VALUE) && p_hilo(x_dtype, B, N, D, M, d_out)) {            // projection: [hi | hi | lo] rows of v.weight
     RefreshJob j{};
     j.type = REFRESH_ROWS; j.src = v_w; j.dst = (char*)workspace + w.w_p;
     j.R = Dp; j.K = D; j.Kp = D; j.ld = D; j.kind = 1; j.bf16 = 1;
     jobs[n++] = j;
   }
-  if (use_tc() && c % 4 == 0) {                        // dP = g . W_m: per-query transposed [hi | hi | lo] rows [m][d][3c]
+  if ((which & EP_REFRESH_VALUE) && use_tc() && c % 4 == 0) {                        // dP = g . W_m: per-query transposed [hi | hi | lo] rows [m][d][3c]
     RefreshJob j{};
     j.type = REFRESH_TRANSPOSE; j.src = v_w; j.dst = (char*)workspace + w.w_t;
     j.K = c; j.Kp = c; j.R = D; j.Z = M; j.src_z = (long long)c * D; j.dst_z = (long long)3 * c * D;
@@ -654,7 +655,7 @@ extern "C" int ep_refresh_operands(const float* cls_token, const float* v_w, flo
     jobs[n++] = j;
   }
   LinWs lw;
-  if (fc_w && K > 0 && lin_ops_ok(Dp, K) && lin_ws(lin_workspace, lin_workspace_bytes, B, Dp, K, &lw)) {
+  if ((which & EP_REFRESH_FC) && fc_w && K > 0 && lin_ops_ok(Dp, K) && lin_ws(lin_workspace, lin_workspace_bytes, B, Dp, K, &lw)) {
     const int Fp = (int)pad64(Dp), Kp = (int)pad64(K);
     RefreshJob j{};                                     // logits: [hi | hi | lo] rows of fc.weight, thirds padded to Fp
     j.type = REFRESH_ROWS; j.src = fc_w; j.dst = lw.w_r;

@@ -68,6 +68,11 @@ class EPHeadTrainer:
         self.fuse_ops = bool(fuse_operands)
         self._ops_key = None                               # parameter versions the weight copies were made from
         self.parallel_dw = os.environ.get("EP_PARALLEL_DW", "1") != "0"
+        # single GPU: v.weight / fc gradients are final after part 1, so their optimizer update and operand refresh run on
+        # the side branch underneath the token-streaming backward; only cls_token's follow it
+        # (measured at c2: 0.598 ms against 0.592 ms without -- nothing can share an SM with the one-pass kernels, so the
+        # early update only delays them; mode 2 forks after the streaming backward instead.  Off by default.)
+        self.split_update = int(os.environ.get("EP_SPLIT_UPDATE", "0"))
         if broadcast_buffers not in ("eval", "step", "off"):
             raise ValueError("broadcast_buffers must be 'eval', 'step' or 'off'")
         if optimizer not in ("lars", "adamw", "sgd"):
@@ -146,10 +151,13 @@ class EPHeadTrainer:
         self.hyper = torch.zeros(8, **f32)                 # so rewriting it for the next step cannot race the GPU
         self._write_hyper()
         self.lars_scratch = torch.empty(8192, **f32)       # EP_LARS_SCRATCH_FLOATS
+        self.lars_scratch2 = torch.empty(8192, **f32)      # (the early group's, when the update runs as two groups)
         self.ce_scratch = torch.zeros(B + 8, **f32)        # per-sample losses + the counter word of ep_ce_fwd_bwd_ops
         self.ws = torch.empty(max(16, self.lib.ep_workspace_bytes(B, N, D, M, self.d_out)), dtype=torch.uint8, device=dev)
         self.lin_ws = torch.empty(max(16, self.lib.ep_linear_workspace_bytes(B, Dp, K)), dtype=torch.uint8, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap_comm else None
+        self._ev_early = torch.cuda.Event() if self.overlap_comm else None
+        self.two_group = os.environ.get("EP_TWO_GROUP_UPDATE", "1") != "0"
         # BatchNorm running statistics as two views of one flat tensor, so that DDP's buffer broadcast is one message
         self.bn_flat = torch.cat([bn.running_mean.detach().reshape(-1), bn.running_var.detach().reshape(-1)]).contiguous()
         bn.running_mean.data = self.bn_flat[:Dp]
@@ -195,14 +203,15 @@ class EPHeadTrainer:
         pointer (in-place tensor ops, ``load_state_dict`` included, are noticed through the tensors' version counters)."""
         self._ops_key = None
 
-    def _refresh_launch(self):
-        """ep_refresh_operands on the current stream (captured into the step's graph right after the optimizer)."""
+    def _refresh_launch(self, which: int = 0):
+        """ep_refresh_operands on the current stream (captured into the step's graph right after the optimizer);
+        which: 0 = every copy, 1 = the queries', 6 = v.weight's and fc.weight's."""
         pool, fc = self.pool, self.fc
         _lib.check(self.lib.ep_refresh_operands(pool.cls_token.data_ptr(), pool.v.weight.data_ptr(), float(pool.scale),
                                                 _lib.x_dtype_code(self.x), self.B, self.N, self.D, self.M, self.d_out,
                                                 self.ws.data_ptr(), self.ws.numel(), fc.weight.data_ptr(), self.K,
-                                                self.lin_ws.data_ptr(), self.lin_ws.numel(), _lib.stream_ptr(self.dev)),
-                   "ep_refresh_operands")
+                                                self.lin_ws.data_ptr(), self.lin_ws.numel(), which,
+                                                _lib.stream_ptr(self.dev)), "ep_refresh_operands")
 
     def _ops_check(self):
         """Make the weight copies current if a parameter changed behind the trainer's back since they were written."""
@@ -233,7 +242,7 @@ class EPHeadTrainer:
                                          self.logits.data_ptr(), lin_ws, lin_n, Wf | If | mode, s), "ep_linear_fwd")
 
     # The step in three stream-ordered parts; the gradient exchange sits between them.
-    def _part1(self):
+    def _part1(self, join: bool = True):
         """forward, loss, and every gradient that does not need the tokens again"""
         lib, s = self.lib, _lib.stream_ptr(self.dev)
         B, N, D, M, Dp, K = self.B, self.N, self.D, self.M, self.Dp, self.K
@@ -280,7 +289,8 @@ class EPHeadTrainer:
             bwd_proj(Wf | If | _lib.EP_OPS_NO_DW, s)
         else:
             bwd_proj(Wf | If, s)
-        cur.wait_stream(self.side_stream)
+        if join:
+            cur.wait_stream(self.side_stream)
 
     def _part2(self):
         """token-streaming half of the backward pass: d cls_token"""
@@ -308,13 +318,23 @@ class EPHeadTrainer:
         if self.fuse_ops:                                  # operand copies of the updated weights for the next step
             self._refresh_launch()
 
-    def _apply_optimizer(self, grads):
+    def _update_group(self, early: bool):
+        """Optimizer + operand refresh for one group of parameters: early = all but cls_token (gradients final after
+        part 1), late = cls_token (its gradient comes out of the token-streaming backward)."""
+        idx = list(range(1, len(self.params))) if early else [0]
+        self._apply_optimizer(self.grads, idx, self.lars_scratch2 if early else self.lars_scratch)
+        if self.fuse_ops:
+            self._refresh_launch(6 if early else 1)
+
+    def _apply_optimizer(self, grads, idx=None, scratch=None):
+        pick = (lambda l: l) if idx is None else (lambda l: [l[i] for i in idx])
         if self.optimizer == "lars":
-            lars_launch(self.params, grads, self.mus, self.trust, self.hyper, self.lars_scratch)
+            lars_launch(pick(self.params), pick(grads), pick(self.mus), pick(self.trust), self.hyper,
+                        self.lars_scratch if scratch is None else scratch)
         elif self.optimizer == "adamw":
-            adamw_launch(self.params, grads, self.mus, self.sq, self.hyper)
+            adamw_launch(pick(self.params), pick(grads), pick(self.mus), pick(self.sq), self.hyper)
         else:
-            sgd_launch(self.params, grads, self.mus if self._mom != 0.0 else None, self.hyper)
+            sgd_launch(pick(self.params), pick(grads), pick(self.mus) if self._mom != 0.0 else None, self.hyper)
 
     def _write_hyper(self):
         """Host scalars of the next optimizer step -> pinned -> device (stream-ordered, no sync)."""
@@ -365,10 +385,63 @@ class EPHeadTrainer:
         else:
             allreduce_sum_(self.flat_grad, self.group)
 
+    # Multi-GPU with overlap: the update runs as two groups so that cls_token's all-reduce (131 KB: pure latency, and
+    # the only exposed collective of the step) hides behind the optimizer update and operand refresh of the early group:
+    #   comm stream:  all-reduce [fc, v]  (under part 2) ............ all-reduce cls_token
+    #   main stream:  part 2 (token-streaming backward) | update early group | (join) update cls_token
+    def _two_group_update(self):
+        return self.world > 1 and self.overlap_comm and self.accum is None and self.two_group
+
+    def _exchange_rest_async(self):
+        """cls_token's all-reduce on the comm stream (behind the early one), main does not wait yet"""
+        cur = torch.cuda.current_stream(self.dev)
+        self._ev_early.record(self.comm_stream)               # the early all-reduce is what main needs first
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            allreduce_sum_(self.flat_grad, self.group, self.n_early)
+        cur.wait_event(self._ev_early)
+
+    def _join_comm(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+
+    def _upd_early(self):
+        self._update_group(early=True)
+
+    def _upd_late(self):
+        self._update_group(early=False)
+
     def _step_body(self):
+        if self.world == 1 and self.accum is None and self.split_update == 2:
+            self._part1()
+            self._part2()
+            cur = torch.cuda.current_stream(self.dev)
+            self.side_stream.wait_stream(cur)
+            with torch.cuda.stream(self.side_stream):
+                self._update_group(early=True)
+            self._update_group(early=False)
+            cur.wait_stream(self.side_stream)
+            return
+        if self.world == 1 and self.accum is None and self.split_update == 1:
+            # one GPU: the early group's update rides on the side branch (behind the weight-gradient GEMMs it depends on),
+            # next to dP and the token-streaming backward; main joins it at the end of the step
+            self._part1(join=False)
+            # (the side branch first waits for main's dP GEMM: it reads the weight copies this update rewrites)
+            self.side_stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(self.side_stream):
+                self._update_group(early=True)
+            self._part2()
+            self._update_group(early=False)
+            torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)
+            return
         self._part1()
         self._exchange_early()
         self._part2()
+        if self._two_group_update():
+            self._exchange_rest_async()
+            self._upd_early()
+            self._join_comm()
+            self._upd_late()
+            return
         self._exchange_rest()
         self._part3()
 
@@ -394,7 +467,9 @@ class EPHeadTrainer:
             # graphs (three graphs per step with the two exchanges between them) -- capturing the
             # collectives inside a graph deadlocked on this stack, and the eager calls cost microseconds.
             one_graph = self.world == 1 or os.environ.get("EP_GRAPH_NCCL", "0") == "1"   # experimental: NCCL captured too
-            parts = [self._step_body] if one_graph else [self._part1, self._part2, self._part3]
+            parts = [self._step_body] if one_graph else \
+                    ([self._part1, self._part2, self._upd_early, self._upd_late] if self._two_group_update() else
+                     [self._part1, self._part2, self._part3])
             graphs = []
             for part in parts:
                 g = torch.cuda.CUDAGraph()
@@ -418,6 +493,14 @@ class EPHeadTrainer:
         self._ops_check()                                   # (after the capture's warm-up step has been rolled back)
         if len(graphs) == 1:
             graphs[0].replay()
+        elif len(graphs) == 4:
+            graphs[0].replay()
+            self._exchange_early()
+            graphs[1].replay()
+            self._exchange_rest_async()
+            graphs[2].replay()
+            self._join_comm()
+            graphs[3].replay()
         else:
             graphs[0].replay()
             self._exchange_early()

@@ -226,12 +226,18 @@ int ep_lars_step(int n, float* const* params_host, const float* const* grads_hos
  * streams (the weight gradient is not needed before the optimizer / the gradient exchange). */
 #define EP_OPS_NO_DW   8
 #define EP_OPS_ONLY_DW 16
-/* Writes every weight-derived operand copy: scale * cls_token as bf16 hi/lo rows, v.weight as [hi|hi|lo] rows and
- * as per-query transposed [hi|hi|lo] rows, fc.weight (K, F = D / d_out) as [hi|hi|lo] rows and transposed.  One
- * launch.  fc_w / lin_workspace may be NULL (pooling head only). */
+/* Writes the weight-derived operand copies: scale * cls_token as bf16 hi/lo rows (EP_REFRESH_QUERIES), v.weight as
+ * [hi|hi|lo] rows and as per-query transposed [hi|hi|lo] rows (EP_REFRESH_VALUE), fc.weight (K, F = D / d_out) as
+ * [hi|hi|lo] rows and transposed (EP_REFRESH_FC).  One launch.  `which` selects the groups (0 = all): a training loop
+ * whose optimizer updates v.weight / fc.weight before the query gradient exists refreshes them early, on another
+ * stream.  fc_w / lin_workspace may be NULL (pooling head only). */
+#define EP_REFRESH_QUERIES 1
+#define EP_REFRESH_VALUE   2
+#define EP_REFRESH_FC      4
+#define EP_REFRESH_ALL     7
 int ep_refresh_operands(const float* cls_token, const float* v_w, float scale, int x_dtype, int B, int N, int D, int M,
                         int d_out, void* workspace, size_t workspace_bytes, const float* fc_w, int K,
-                        void* lin_workspace, size_t lin_workspace_bytes, void* stream);
+                        void* lin_workspace, size_t lin_workspace_bytes, int which, void* stream);
 int ep_fwd_ops(const void* x, int x_dtype, const float* cls_token, const float* v_w, const float* v_b,
                float scale, int B, int N, int D, int M, int d_out,
                float* out, float* S, float* rowmax, float* rowsum, float* P, float* attn,
