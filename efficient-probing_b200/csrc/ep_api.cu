@@ -4,6 +4,7 @@
 #include "ep_sm100.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace ep;
 
@@ -20,6 +21,15 @@ struct OpsScope {                             // per-call, per-thread GEMM mode 
   ~OpsScope() { t_fp32_gemm = saved; }
 };
 }  // namespace
+
+bool ep::pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("EP_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 
 extern "C" int ep_abi_version(void) { return EP_ABI_VERSION; }
 

@@ -41,6 +41,28 @@ inline int stream_sms() { const int n = num_sms(); return g_sm_limit > 0 && g_sm
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// The kernels of a training step form one dependent chain on one stream; launched with the programmatic-stream-
+// serialization attribute a kernel may be scheduled while its predecessor is still draining, run its prologue (barrier
+// init, TMEM allocation, tensor-map prefetch, shared-memory clears) and then block in pdl_wait() until the predecessor
+// grid has completed and its writes are visible.  Every kernel launched through launch_pdl() calls pdl_wait() before
+// its first global-memory access and pdl_trigger() right at its start (dependents may be scheduled as soon as every
+// CTA of this grid is running).  Without the attribute both instructions are no-ops.  EP_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // round-to-nearest fp32 -> tf32 (10-bit mantissa): operands of the TF32 tensor-core GEMMs are stored
 // pre-rounded so that the hardware's truncation of the low bits is exact (no bias)
 __device__ __forceinline__ float round_tf32(float v) {

@@ -28,6 +28,8 @@ bn_fwd_kernel(const float* __restrict__ h, int B, int F, float eps, float moment
   // y3 (nullable): the [hi | lo | hi] bf16 operand copy of y, rows of 3 Fp (thirds zero-padded from F to Fp; the grid
   // then covers Fp features) -- what the tcgen05 classifier GEMM reads (ep_linear_fwd_ops)
   __shared__ float red[BN_Y][BN_F + 1];
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
   float mean, invstd;
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(BN_F * BN_Y)
 bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ invstd, int B, int F,
               float* __restrict__ dh) {
   __shared__ float red[BN_Y][BN_F + 1];
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.x * BN_F + threadIdx.x;
   const bool ok = f < F;
   float s1 = 0.f, s2 = 0.f;
@@ -142,6 +146,8 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target
   // rows in a fixed order, OVERWRITES loss_sum[0] and adds the value to loss_acc (no zeroing, deterministic)
   __shared__ float redf[8];
   __shared__ int redi[8];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* row = logits + (size_t)b * K;
   // the row stays in registers between the passes when K <= 1024 (4 values per thread: one load, one exp per element)
@@ -259,6 +265,8 @@ struct LarsArgs {
 
 // deterministic norms: every CTA writes its partial sums, the update kernel adds them in a fixed order
 __global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float* __restrict__ hyper, float* partial, int vec) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.y;
   if (!a.trust[t]) return;
   const float wd = hyper[1], gs = hyper[4];
@@ -298,6 +306,8 @@ __global__ void __launch_bounds__(256) lars_norm_kernel(LarsArgs a, const float*
 
 __global__ void __launch_bounds__(256) lars_update_kernel(LarsArgs a, const float* __restrict__ hyper,
                                                           const float* __restrict__ partial, int vec) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.y;
   const float lr = hyper[0], wd = hyper[1], mom = hyper[2], tc = hyper[3], gs = hyper[4];
   __shared__ float qs;
@@ -450,21 +460,21 @@ int ep::launch_bn_fwd(const float* h, int B, int F, float eps, float momentum, i
                       float* running_var, long long* nbt, float* y, float* save_mean, float* save_invstd, void* y3, int Fp,
                       cudaStream_t s) {
   const int cols = y3 ? Fp : F;
-  bn_fwd_kernel<<<(cols + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, s>>>(h, B, F, eps, momentum, training, running_mean, running_var,
-                                                                    nbt, y, save_mean, save_invstd, (__nv_bfloat16*)y3, Fp);
+  EP_CUDA(launch_pdl(bn_fwd_kernel, dim3((cols + BN_F - 1) / BN_F), dim3(BN_F, BN_Y), 0, s, h, B, F, eps, momentum, training,
+                     running_mean, running_var, nbt, y, save_mean, save_invstd, (__nv_bfloat16*)y3, Fp));
   EP_LAUNCH_CHECK();
   return 0;
 }
 int ep::launch_bn_bwd(const float* dy, const float* y, const float* save_invstd, int B, int F, float* dh, cudaStream_t s) {
-  bn_bwd_kernel<<<(F + BN_F - 1) / BN_F, dim3(BN_F, BN_Y), 0, s>>>(dy, y, save_invstd, B, F, dh);
+  EP_CUDA(launch_pdl(bn_bwd_kernel, dim3((F + BN_F - 1) / BN_F), dim3(BN_F, BN_Y), 0, s, dy, y, save_invstd, B, F, dh));
   EP_LAUNCH_CHECK();
   return 0;
 }
 int ep::launch_ce(const float* logits, const long long* targets, int B, int K, float loss_scale, float grad_scale,
                   float* loss_sum, float* dlogits, int* correct, void* d3, int Kp, float* scratch, float* loss_acc,
                   cudaStream_t s) {
-  ce_kernel<<<B, 256, 0, s>>>(logits, targets, K, loss_scale, grad_scale, loss_sum, dlogits, correct, (__nv_bfloat16*)d3, Kp,
-                              scratch, loss_acc);
+  EP_CUDA(launch_pdl(ce_kernel, dim3(B), dim3(256), 0, s, logits, targets, K, loss_scale, grad_scale, loss_sum, dlogits, correct,
+                     (__nv_bfloat16*)d3, Kp, scratch, loss_acc));
   EP_LAUNCH_CHECK();
   return 0;
 }
@@ -502,9 +512,9 @@ extern "C" int ep_lars_step(int n, float* const* params, const float* const* gra
   int bx = (int)((mx + 256 * 8 - 1) / (256 * 8));
   if (bx < 1) bx = 1;
   if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;                  // 2 * n * bx <= EP_LARS_SCRATCH_FLOATS
-  lars_norm_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch, vec);
+  EP_CUDA(launch_pdl(lars_norm_kernel, dim3(bx, n), dim3(256), 0, s, a, hyper, scratch, vec));
   EP_LAUNCH_CHECK();
-  lars_update_kernel<<<dim3(bx, n), 256, 0, s>>>(a, hyper, scratch, vec);
+  EP_CUDA(launch_pdl(lars_update_kernel, dim3(bx, n), dim3(256), 0, s, a, hyper, (const float*)scratch, vec));
   EP_LAUNCH_CHECK();
   return 0;
 }

@@ -72,6 +72,7 @@
 
 #include <algorithm>
 
+#include "ep_common.cuh"
 #include "ep_ptx.cuh"
 #include "ep_sm100.cuh"
 
@@ -218,10 +219,12 @@ fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   // operand blocks start as zeros: rows m >= M and tokens that no epilogue thread owns stay zero for the whole launch
   for (uint32_t o = threadIdx.x * 16u; o < blk_bytes; o += kThreadsF * 16u)
     *reinterpret_cast<uint4*>(gen + (blk_base - ring) + o) = make_uint4(0, 0, 0, 0);
+  pdl_trigger();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();       // everything above is CTA-local set-up; the tokens' companions (queries, dP, statistics) come from the previous kernel
   const uint32_t tmem_base = *tmem_slot_ptr;
   // this CTA's samples, d-chunks [c_lo, c_lo + nch) and d-slices [sl_lo, sl_lo + nslh)
   const int cta = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -1033,10 +1036,10 @@ int launch_fused(const void* x, const void* w, int w_batched, int J, int B, int 
   p.bufcols = pl.bufcols; p.pcol0 = pl.pcol0; p.tmem_cols = pl.tmem_cols; p.w_batched = w_batched; p.qoff = pl.qoff; p.toff = pl.toff;
   if (p.trace || p.nomma || p.noepi || p.pair || p.skip) {                  // developer knobs: the instrumented instantiation
     if ((rc = set_smem(fused_kernel<kBwd, true>, pl.smem))) return rc;
-    fused_kernel<kBwd, true><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
+    EP_CUDA(launch_pdl(fused_kernel<kBwd, true>, dim3(grid), dim3(kThreadsF), pl.smem, s, tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p));
   } else {
     if ((rc = set_smem(fused_kernel<kBwd, false>, pl.smem))) return rc;
-    fused_kernel<kBwd, false><<<grid, kThreadsF, pl.smem, s>>>(tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p);
+    EP_CUDA(launch_pdl(fused_kernel<kBwd, false>, dim3(grid), dim3(kThreadsF), pl.smem, s, tm_x, tm_x1, tm_xt, tm_b, tm_bl, tm_w, p));
   }
   EP_LAUNCH_CHECK();
   return 0;

@@ -111,9 +111,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a); prefetch_tmap(&tm_b); }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                                  // the operands are another kernel's output: from here on
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int gk = g.bf16 ? 2 * kGK : kGK;                      // elements per 128-byte row = K elements per stage
   const int nk = (g.K + gk - 1) / gk;
@@ -324,7 +326,7 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GemmTC g, i
   EP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   g.Z = Z;
   const int ntiles = ((g.J + g.NT - 1) / g.NT) * ((g.I + 127) / 128) * Z;
-  gemm_tf32_kernel<<<std::min(ntiles, kNumSMs), 384, smem, s>>>(tm_a, tm_b, g);
+  EP_CUDA(launch_pdl(gemm_tf32_kernel, dim3(std::min(ntiles, kNumSMs)), dim3(384), smem, s, tm_a, tm_b, g));
   EP_LAUNCH_CHECK();
   return 0;
 }

@@ -119,6 +119,8 @@ struct RefreshArgs {
 
 __global__ void __launch_bounds__(256) refresh_kernel(const RefreshArgs a) {
   __shared__ float tile[32][33];
+  pdl_trigger();
+  pdl_wait();
   int q = 0;
   while (q + 1 < a.n && (int)blockIdx.x >= a.begin[q + 1]) ++q;
   const RefreshJob& j = a.job[q];
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(256)
 g_ops_kernel(const float* __restrict__ g, const float* __restrict__ out, const float* __restrict__ bias, int B, int M, int c,
              float* __restrict__ delta, void* __restrict__ g3, int g3_bf16, __nv_bfloat16* __restrict__ g3t) {
   __shared__ float tile[32][33];                                   // [sample][channel] of the current chunk
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b0 = blockIdx.x * 32, m = blockIdx.y;
   const int Dp = M * c;
@@ -221,14 +225,15 @@ int launch_refresh(const RefreshJob* jobs, int n, cudaStream_t s) {
     total += (int)std::max<long long>(1, nb);
   }
   a.begin[n] = total;
-  refresh_kernel<<<total, 256, 0, s>>>(a);
+  EP_CUDA(launch_pdl(refresh_kernel, dim3(total), dim3(256), 0, s, a));
   EP_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_g_ops(const float* g, const float* out, const float* bias, int B, int M, int c, float* delta, void* g3,
                  int g3_bf16, void* g3t, cudaStream_t s) {
-  g_ops_kernel<<<dim3((B + 31) / 32, M), 256, 0, s>>>(g, out, bias, B, M, c, delta, g3, g3_bf16, (__nv_bfloat16*)g3t);
+  EP_CUDA(launch_pdl(g_ops_kernel, dim3((B + 31) / 32, M), dim3(256), 0, s, g, out, bias, B, M, c, delta, g3, g3_bf16,
+                     (__nv_bfloat16*)g3t));
   EP_LAUNCH_CHECK();
   return 0;
 }

@@ -695,6 +695,8 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t n,
                                                               float scale, float* __restrict__ out) {
   __shared__ float sm[8][33];
+  pdl_trigger();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const size_t i = (size_t)blockIdx.x * 32 + tx;
   float s = 0.f;
@@ -976,7 +978,8 @@ int sm100_pool_bwd(const void* x, const float* S, float scale, int B, int N, int
     tm.mark("kp<1> dq");
   }
   const size_t n = (size_t)M * D;
-  reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(part, groups, n, scale, d_cls);
+  EP_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)((n + 31) / 32)), dim3(256), 0, s, (const float*)part, groups, n, scale,
+                     d_cls));
   EP_LAUNCH_CHECK();
   tm.mark("reduce");
   return 0;
