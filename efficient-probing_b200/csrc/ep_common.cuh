@@ -46,8 +46,10 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // serialization attribute a kernel may be scheduled while its predecessor is still draining, run its prologue (barrier
 // init, TMEM allocation, tensor-map prefetch, shared-memory clears) and then block in pdl_wait() until the predecessor
 // grid has completed and its writes are visible.  Every kernel launched through launch_pdl() calls pdl_wait() before
-// its first global-memory access and pdl_trigger() right at its start (dependents may be scheduled as soon as every
-// CTA of this grid is running).  Without the attribute both instructions are no-ops.  EP_PDL=0 turns the attribute off.
+// its first global-memory access.  pdl_trigger() (dependents may be scheduled once every CTA of this grid has called
+// it) sits at the start of the short kernels and at the END of the persistent ones (one-pass pooling kernels, GEMMs):
+// triggered early, a dependent's CTAs would occupy whatever SMs a long kernel leaves free and starve other streams.
+// Without the attribute both instructions are no-ops.  EP_PDL=0 turns the attribute off.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();

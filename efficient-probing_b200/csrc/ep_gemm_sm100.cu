@@ -111,7 +111,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a); prefetch_tmap(&tm_b); }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
-  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -278,6 +277,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  pdl_trigger();                                               // (at the end: see ep_fused_sm100.cu)
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 

@@ -17,5 +17,5 @@ except Exception as e:
 PY
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02b_ncu_launch_list.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_ll.log 2>&1
-python tools/summarize_launch_list.py gpurun_out/r02b_ncu_launch_list.csv 17 > gpurun_out/r02b_ncu_launch_list_summary.txt; tail -3 gpurun_out/r02b_ncu_launch_list_summary.txt
+python tools/summarize_launch_list.py gpurun_out/r02b_ncu_launch_list.csv 17 auto > gpurun_out/r02b_ncu_launch_list_summary.txt; tail -3 gpurun_out/r02b_ncu_launch_list_summary.txt
 timeout 600 compute-sanitizer --tool memcheck python tools/dev_memcheck_step.py > gpurun_out/r02b_compute_sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/r02b_compute_sanitizer_memcheck.log

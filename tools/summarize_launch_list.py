@@ -1,5 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: the launches of the LAST step in order and
-per kernel (python tools/summarize_launch_list.py launches.csv launches_per_step)."""
+per kernel (python tools/summarize_launch_list.py launches.csv launches_per_step [first launch]); without a first launch
+the last `launches_per_step` launches are taken, with `auto` the second run of launches that starts at a one-pass /
+logit kernel of the forward (one full training step after warm-up)."""
 import csv, sys
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if not l.startswith("=="))]
 h = rows[0]
@@ -13,7 +15,14 @@ for r in rows[1:]:
     us = v / 1e3 if u in ("ns", "nsecond") else v * 1e3 if u in ("ms", "msecond") else v
     L.append((r[ki].split("(")[0][:64], us))
 n = int(sys.argv[2]) if len(sys.argv) > 2 else len(L)
-last = L[-n:]
+if len(sys.argv) > 3 and sys.argv[3] == "auto":
+    starts = [i for i, (k, _) in enumerate(L) if "fused_kernel<0" in k or "ks_kernel<2" in k or "ks_kernel<0" in k]
+    first = starts[1] if len(starts) > 1 else starts[0]
+    last = L[first:first + n]
+elif len(sys.argv) > 3:
+    last = L[int(sys.argv[3]):int(sys.argv[3]) + n]
+else:
+    last = L[-n:]
 tot = sum(u for _, u in last)
 print(f"{n} launches, {tot:.1f} us summed (cold-cache, serialised: shares, not absolutes)\n\nin launch order:")
 for k, u in last:
