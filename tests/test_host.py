@@ -46,6 +46,22 @@ def test_argument_rejection_needs_no_gpu():
     assert L.ep_pooled_layout(1, 64, 19, 128, 8, 1) == 0         # fp32 tokens: general kernels, fp32 P
     assert L.ep_set_sm_limit(-1) == -2 and L.ep_set_sm_limit(0) == 0
     assert L.ep_linear_workspace_bytes(8, 72, 10) >= 3 * 2 * (10 * 128 + 72 * 64 + 8 * 128 + 8 * 64)   # padded thirds
+    # ABI 2 (*_ops variants): the same checks in front of any CUDA call
+    assert L.ep_fwd_ops(None, 0, None, None, None, 1.0, 1, 1, 8, 1, 1, None, None, None, None, None, None, None, 0, 3, None) == -1
+    assert L.ep_refresh_operands(None, None, 1.0, 0, 4, 19, 64, 8, 1, None, 0, None, 10, None, 0, 0, None) == -1
+    one = ctypes.c_float(0.0)
+    ptr = ctypes.cast(ctypes.pointer(one), ctypes.c_void_p)                       # any non-NULL address: rejected on shape / size
+    assert L.ep_refresh_operands(ptr, ptr, 1.0, 0, 4, 19, 64, 5, 1, ptr, 1 << 30, None, 10, None, 0, 0, None) == -2   # 64 % 5
+    assert L.ep_refresh_operands(ptr, ptr, 1.0, 0, 4, 19, 64, 8, 1, ptr, 16, None, 10, None, 0, 0, None) == -5         # workspace
+    assert L.ep_bwd_proj_ops(None, None, None, None, None, 0, 4, 19, 64, 8, 1, None, None, None, 0, 3, None) == -1
+    assert L.ep_bwd_proj_ops(ptr, ptr, ptr, ptr, None, 0, 4, 19, 64, 8, 1, ptr, None, ptr, 16, 3, None) == -5
+    assert L.ep_bn_fwd_ops(None, 4, 8, 1e-6, 0.1, 1, None, None, None, None, None, None, 10, None, 0, 0, None) == -1
+    assert L.ep_bn_bwd_ops(None, None, None, 4, 8, None, None, None, 0, 19, 64, 8, 1, None, 0, 0, None) == -1
+    assert L.ep_bn_bwd_ops(ptr, ptr, ptr, 4, 9, ptr, ptr, None, 0, 19, 64, 8, 1, ptr, 1 << 30, 0, None) == -2          # F != D / d_out
+    assert L.ep_linear_fwd_ops(None, None, None, 4, 8, 10, None, None, 0, 3, None) == -1
+    assert L.ep_linear_bwd_ops(None, None, None, 4, 8, 10, None, None, None, None, 0, 3, None) == -1
+    assert L.ep_ce_fwd_bwd_ops(None, None, 4, 10, 1.0, 1.0, None, None, None, None, None, 8, None, 0, 0, None) == -1
+    assert L.ep_ce_fwd_bwd_ops(ptr, ptr, 4, 10, 1.0, 1.0, ptr, None, None, None, None, 8, None, 0, 0, None) == -1      # scratch is required
 
 
 def test_module_surface_matches_reference_fingerprints():
